@@ -1,0 +1,184 @@
+/*
+ * srb200.h — C ABI of libsrb200.so: the B200 (sm_100a) drop-in for SingleRust's sparse count-matrix
+ * analytics path. Plain pointers and sizes only; every function returns an srb_status (0 = OK) and never
+ * aborts or throws across the boundary; srb_last_error_message() gives the thread-local reason.
+ *
+ * The reference (pure Rust, /root/reference) has no FFI boundary; the seam sits where it hands raw
+ * CSR/CSC slices (nalgebra-sparse row_offsets()/col_indices()/values(), `usize` = u64) to arithmetic.
+ * Each entry point cites the reference function whose body it replaces. INTEGRATION.md shows the
+ * Rust `extern "C"` block that binds these symbols 1:1.
+ *
+ * Model: upload once -> many ops on the device-resident matrix -> download. One srb_ctx = one GPU + one
+ * CUDA stream (+ optionally one NCCL rank of a cell-row-sharded job). Calls on one ctx are serialised
+ * by the caller (mirrors the RwLock in anndata-memory's IMArrayElement, src/memory/statistics/mod.rs:12).
+ */
+#ifndef SRB200_H
+#define SRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRB_VERSION_MAJOR 0
+#define SRB_VERSION_MINOR 1
+
+typedef enum srb_status {
+    SRB_OK = 0,
+    SRB_ERR_INVALID_ARG = -1,
+    SRB_ERR_UNSUPPORTED_DTYPE = -2, /* I64/U64/Usize/Bool/String: the reference panics, shared/mod.rs:117-126 */
+    SRB_ERR_INDEX_OOB = -3,
+    SRB_ERR_CUDA = -4,
+    SRB_ERR_NCCL = -5,
+    SRB_ERR_OOM = -6,
+    SRB_ERR_NAN = -7,        /* NaN variance in HVG sort: the reference panics, dim_red/mod.rs:138 */
+    SRB_ERR_UNSUPPORTED = -8 /* container/op combination the reference answers with todo!() */
+} srb_status;
+
+/* src/shared/mod.rs:39-42 — identical discriminants */
+typedef enum srb_direction { SRB_ROW = 0, SRB_COLUMN = 1 } srb_direction;
+
+/* anndata DynCsrMatrix / DynCscMatrix variants accepted by match_dyn_cs{r,c}_matrix!, shared/mod.rs:110-150 */
+typedef enum srb_dtype {
+    SRB_I8 = 0, SRB_I16 = 1, SRB_I32 = 2, SRB_I64 = 3, /* I64: unsupported */
+    SRB_U8 = 4, SRB_U16 = 5, SRB_U32 = 6, SRB_U64 = 7, /* U64: unsupported */
+    SRB_F32 = 8, SRB_F64 = 9
+} srb_dtype;
+
+typedef enum srb_format { SRB_CSR = 0, SRB_CSC = 1 } srb_format;
+
+/* width of the host offset/index integers: 8 = Rust usize (nalgebra-sparse), 4 = h5ad on-disk int32 */
+typedef enum srb_index_width { SRB_IDX32 = 4, SRB_IDX64 = 8 } srb_index_width;
+
+/* value storage policy after normalize_total / log1p:
+ *   COMPACT  keep f32 storage when the input was f32-representable (halves HBM traffic; |rel err| <= 2e-7)
+ *   FAITHFUL promote to f64 exactly like the reference does (scale/mod.rs:74-83, transform/mod.rs:48-55) */
+typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } srb_value_mode;
+
+typedef struct srb_ctx srb_ctx;
+typedef struct srb_mat srb_mat;
+
+/* ---- library ------------------------------------------------------------------------------------ */
+const char *srb_version(void);
+const char *srb_last_error_message(void);
+/* number of CUDA kernels launched by this library on the calling process since load (bench "gpu_launches") */
+uint64_t srb_kernel_launch_count(void);
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int32_t srb_ctx_create(int32_t device, srb_ctx **out);
+int32_t srb_ctx_destroy(srb_ctx *ctx);
+int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode /* srb_value_mode */);
+int32_t srb_ctx_synchronize(srb_ctx *ctx);
+/* the cudaStream_t all work of this ctx is enqueued on (for CUDA-event timing by the caller) */
+void *srb_ctx_stream(srb_ctx *ctx);
+
+/* multi-GPU (new; the reference is single-process): one rank per GPU, matrix sharded by cell-row.
+ * id128 is an ncclUniqueId (128 bytes) produced by srb_comm_unique_id on rank 0 and broadcast by the
+ * launcher (bench.py uses torch.distributed for that rendezvous only). */
+int32_t srb_comm_unique_id(void *id128);
+int32_t srb_ctx_comm_init(srb_ctx *ctx, const void *id128, int32_t rank, int32_t nranks);
+
+/* ---- matrix upload / download ------------------------------------------------------------------- */
+/* Borrow host arrays for the duration of the call (Rust holds the read guard) and build the device copy.
+ * offsets[nmajor+1], indices[nnz] of width idx_width; values[nnz] of `dtype`.
+ * Indices must be < nminor (else SRB_ERR_INDEX_OOB, checked on device). Replaces nothing in the reference;
+ * it is the residency step in front of every function below.
+ * global_row0 / global_nrows describe this rank's shard of a row-sharded CSR (pass 0 / nrows when unsharded). */
+int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t ncols, uint64_t nnz,
+                       const void *offsets, const void *indices, int32_t idx_width, const void *values,
+                       int32_t dtype, srb_mat **out);
+int32_t srb_mat_set_shard(srb_mat *m, uint64_t global_row0, uint64_t global_nrows);
+int32_t srb_mat_free(srb_mat *m);
+/* deep copy (IMAnnData::deep_clone used by normalize_total / log1p_transform, processing/mod.rs:314-332);
+ * the index structure is shared (immutable), values are copied */
+int32_t srb_mat_clone(srb_mat *m, srb_mat **out);
+int32_t srb_mat_info(srb_mat *m, uint64_t *nrows, uint64_t *ncols, uint64_t *nnz, int32_t *format,
+                     int32_t *value_dtype /* SRB_F32 or SRB_F64: current device storage */);
+/* current values as f64 (what the reference holds after normalise) or f32; any of the pointers may be NULL */
+int32_t srb_mat_download(srb_mat *m, uint64_t *offsets, uint64_t *indices, double *values_f64, float *values_f32);
+
+/* synthetic count matrix generated on the device (bit-identical to oracle/srb_oracle.c
+ * orc_synth_*): rows [row0, row0+nrows) of the global matrix for `seed`; thr/amp are host tables of ncols. */
+int32_t srb_synth_csr(srb_ctx *ctx, uint32_t seed, int32_t skew, uint64_t row0, uint64_t nrows, uint32_t ncols,
+                      const uint32_t *thr, const uint32_t *amp, srb_mat **out);
+
+/* ---- statistics: shared::statistics::{number,sum,variance,minmax,stddev}::whole ------------------- */
+/* All outputs are caller-allocated host buffers of length nrows (SRB_ROW) or ncols (SRB_COLUMN).
+ * On a sharded matrix, SRB_ROW outputs cover the local rows; SRB_COLUMN outputs are allreduced. */
+/* number_whole_helper: csr.rs:16-38, csc.rs:15-35 (counts stored entries incl. explicit zeros) */
+int32_t srb_number(srb_mat *m, int32_t direction, uint32_t *out);
+/* sum_whole_helper: csr.rs:81-102, csc.rs:74-95 */
+int32_t srb_sum(srb_mat *m, int32_t direction, double *out);
+/* variance_whole_helper: csr.rs:149-188, csc.rs:137-176 (nonzero-only; major two-pass/NaN, minor one-pass/0) */
+int32_t srb_variance(srb_mat *m, int32_t direction, double *out);
+/* std_dev_whole: csr.rs:225-228, csc.rs:213-216 */
+int32_t srb_std_dev(srb_mat *m, int32_t direction, double *out);
+/* min_max_whole_helper: csr.rs:194-223, csc.rs:182-211 (empty line -> +inf / -inf) */
+int32_t srb_min_max(srb_mat *m, int32_t direction, double *out_min, double *out_max);
+/* compute_qc_variables, memory/statistics/mod.rs:48-72: the 8 vectors of StatisticsContainer in one call
+ * (two passes over the matrix instead of the reference's sixteen). Any pointer may be NULL. */
+int32_t srb_qc_all(srb_mat *m, uint32_t *num_per_cell, uint32_t *num_per_gene, double *expr_per_cell,
+                   double *expr_per_gene, double *variance_per_cell, double *variance_per_gene,
+                   double *std_dev_per_cell, double *std_dev_per_gene);
+
+/* ---- chunked accumulation: shared::statistics::{number,sum}::chunked (mod.rs:17-41, 59-83) --------- */
+/* Streaming accumulator for backed (out-of-core) data. Push row-chunks (CSR) or column-chunks (CSC) in
+ * order; the major offset of each chunk is tracked, so SRB_ROW results land at the correct global row
+ * (the reference drops the offset: csr.rs:56-61,125-127 — documented deviation). */
+typedef struct srb_stream srb_stream;
+int32_t srb_stream_begin(srb_ctx *ctx, int32_t format, uint64_t nrows_total, uint64_t ncols_total, srb_stream **out);
+int32_t srb_stream_push(srb_stream *s, uint64_t nmajor_chunk, uint64_t nnz, const void *offsets, const void *indices,
+                        int32_t idx_width, const void *values, int32_t dtype);
+int32_t srb_stream_number(srb_stream *s, int32_t direction, uint32_t *out);
+int32_t srb_stream_sum(srb_stream *s, int32_t direction, double *out);
+int32_t srb_stream_variance(srb_stream *s, int32_t direction, double *out); /* new: not in the reference */
+int32_t srb_stream_free(srb_stream *s);
+
+/* ---- normalisation / transform -------------------------------------------------------------------- */
+/* normalize_total_inplace -> scale_row / scale_col: processing/mod.rs:303-312, scale/mod.rs:7-173.
+ * scale = 0 if line sum == 0 else target/sum. Deferred: the multiply is fused into the next pass that
+ * touches the values (DESIGN.md "deferred transforms"); results are identical to eager execution. */
+int32_t srb_normalize_total_inplace(srb_mat *m, double target_sum, int32_t direction);
+/* log1p_transform_inplace -> log1p_data: processing/mod.rs:324-326, transform/mod.rs:8-62 */
+int32_t srb_log1p_inplace(srb_mat *m);
+
+/* ---- feature selection: select_features, dim_red/mod.rs:123-156 ------------------------------------ */
+/* HighlyVariable(n_top): indices in DESCENDING-variance order, ties by ascending index (stable sort).
+ * *out_n = min(n_top, ncols). SRB_ERR_NAN if a variance is NaN (reference panics). */
+int32_t srb_select_hvg(srb_mat *m, uint64_t n_top, uint64_t *out_idx, uint64_t *out_n);
+/* VarianceThreshold(t): v > t, ascending index order */
+int32_t srb_select_var_threshold(srb_mat *m, double threshold, uint64_t *out_idx, uint64_t *out_n);
+
+/* ---- selected densify: convert_to_array_f64_selected, shared/mod.rs:230-315 ------------------------ */
+/* all rows x selected columns, row-major f64, column j = col_sel[j]; parity/debug use (16 GB at 1M x 2000) */
+int32_t srb_densify_selected(srb_mat *m, const uint64_t *col_sel, uint64_t n_sel, double *out);
+
+/* ---- PCA: pca_inplace, dim_red/mod.rs:24-94 (+ single_algebra PCABuilder fit/transform) ------------- */
+/* col_sel/n_sel: the selected features in selection order (from srb_select_hvg or the caller);
+ * k = n_components (capped at n_sel like dim_red/mod.rs:52). center/scale as PCABuilder.
+ * Outputs (host, any may be NULL): scores local_rows x k row-major (obsm["X_pca"]); components n_sel x k
+ * row-major (V[:, :k], rows in selection order); explained_variance_ratio k.
+ * gram_mode: 0 = tensor cores (tcgen05, split-fp16 operands, fp32 TMEM chunks, fp64 across chunks),
+ *            1 = fp64 CUDA-core reference path (validation). */
+int32_t srb_pca(srb_mat *m, const uint64_t *col_sel, uint64_t n_sel, uint64_t k, int32_t center, int32_t scale,
+                int32_t gram_mode, double *scores, double *components, double *explained_variance_ratio);
+
+/* One call for the headline pipeline on a raw-count matrix (BASELINE.json config 3):
+ * normalize_total_inplace(target, Row) -> log1p_transform_inplace -> pca_inplace(HighlyVariable(n_top), k).
+ * Equivalent to the three calls above; exists so a host can enqueue the whole step without intermediate
+ * host round-trips. hvg_out receives the selection (n_top entries). */
+int32_t srb_pipeline_normalize_hvg_pca(srb_mat *m, double target_sum, uint64_t n_top, uint64_t k, int32_t center,
+                                       int32_t scale, int32_t gram_mode, uint64_t *hvg_out, double *scores,
+                                       double *components, double *explained_variance_ratio);
+
+/* per-stage device times (ms) of the last srb_pca / srb_pipeline_* call on this matrix's ctx, measured with
+ * CUDA events on the ctx stream: [0] row sums, [1] fused normalise+log1p+gene moments, [2] hvg select,
+ * [3] densify, [4] gram, [5] eig, [6] scores, [7] allreduce. n = capacity of out_ms. */
+int32_t srb_last_stage_ms(srb_ctx *ctx, float *out_ms, int32_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H */

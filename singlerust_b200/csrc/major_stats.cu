@@ -1,0 +1,153 @@
+// major_stats.cu — K1: segmented reductions along the MAJOR axis of a compressed matrix (per cell on CSR,
+// per gene on CSC). Replaces the Row branches of src/shared/statistics/helper/csr.rs (sum 87-93, variance
+// 158-170, min/max 200-210) and the Column branches of helper/csc.rs.
+//
+// HBM-bound: 4 B/nnz (f32 values) + 8 B/line of offsets; column indices are never read.
+// Mapping: LPR lanes cooperate on one line (LPR = 32 for long lines, 8 for short ones), coalesced strided
+// loads with 4 independent loads in flight per lane, f64 accumulation, shuffle tree at the end.
+#include "common.cuh"
+
+namespace srb {
+
+enum { MODE_SUM_ABSMAX = 0, MODE_VARIANCE = 1, MODE_MINMAX = 2 };
+
+template <int LPR>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int LPR>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int LPR>
+__device__ __forceinline__ double group_min(double v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+template <typename VT, int LPR, int MODE>
+__global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__restrict__ off, const VT *__restrict__ val,
+                                                           uint64_t nmajor, double *__restrict__ o0,
+                                                           double *__restrict__ o1, uint32_t *__restrict__ flags) {
+    const int lane = threadIdx.x % LPR;
+    const uint64_t group = ((uint64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
+    const uint64_t ngroups = (uint64_t)gridDim.x * 256 / LPR;
+    const uint64_t iters = (nmajor + ngroups - 1) / ngroups;  // uniform trip count: shuffles stay convergent
+    uint32_t bad = 0;
+    for (uint64_t it = 0; it < iters; ++it) {
+        const uint64_t i = group + it * ngroups;
+        const bool act = i < nmajor;
+        const int64_t a = act ? off[i] : 0;
+        const int64_t b = act ? off[i + 1] : 0;
+        if (MODE == MODE_SUM_ABSMAX || MODE == MODE_VARIANCE) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mx = 0;
+            int64_t k = a + lane;
+            for (; k + 3 * LPR < b; k += 4 * LPR) {
+                const double v0 = (double)val[k], v1 = (double)val[k + LPR], v2 = (double)val[k + 2 * LPR],
+                             v3 = (double)val[k + 3 * LPR];
+                s0 += v0, s1 += v1, s2 += v2, s3 += v3;
+                if (MODE == MODE_SUM_ABSMAX) {
+                    mx = fmax(fmax(mx, fabs(v0)), fmax(fabs(v1), fmax(fabs(v2), fabs(v3))));
+                    bad |= (v0 < 0) | (v1 < 0) | (v2 < 0) | (v3 < 0);
+                    bad |= 2u * (!isfinite(v0) | !isfinite(v1) | !isfinite(v2) | !isfinite(v3));
+                }
+            }
+            for (; k < b; k += LPR) {
+                const double v0 = (double)val[k];
+                s0 += v0;
+                if (MODE == MODE_SUM_ABSMAX) {
+                    mx = fmax(mx, fabs(v0));
+                    bad |= (v0 < 0) | (2u * !isfinite(v0));
+                }
+            }
+            const double sum = group_sum<LPR>((s0 + s1) + (s2 + s3));
+            if (MODE == MODE_SUM_ABSMAX) {
+                mx = group_max<LPR>(mx);
+                if (act && lane == 0) {
+                    o0[i] = sum;
+                    o1[i] = mx;
+                }
+            } else {
+                // variance_whole_helper major branch: mean = sum/count; sum((v-mean)^2)/count; 0/0 -> NaN
+                const double cnt = (double)(uint32_t)(b - a);
+                const double mean = sum / cnt;
+                double q0 = 0, q1 = 0;
+                int64_t k2 = a + lane;
+                for (; k2 + LPR < b; k2 += 2 * LPR) {
+                    const double d0 = (double)val[k2] - mean, d1 = (double)val[k2 + LPR] - mean;
+                    q0 += d0 * d0, q1 += d1 * d1;
+                }
+                for (; k2 < b; k2 += LPR) {
+                    const double d0 = (double)val[k2] - mean;
+                    q0 += d0 * d0;
+                }
+                const double ss = group_sum<LPR>(q0 + q1);
+                if (act && lane == 0) o0[i] = ss / cnt;
+            }
+        } else {
+            double mn = INFINITY, mx = -INFINITY;
+            for (int64_t k = a + lane; k < b; k += LPR) {
+                const double v = (double)val[k];
+                mn = fmin(mn, v), mx = fmax(mx, v);
+            }
+            mn = group_min<LPR>(mn), mx = group_max<LPR>(mx);
+            if (act && lane == 0) {
+                o0[i] = mn;
+                o1[i] = mx;
+            }
+        }
+    }
+    if (MODE == MODE_SUM_ABSMAX && bad) atomicOr(flags, bad & 1u), atomicOr(flags + 1, (bad >> 1) & 1u);
+}
+
+template <int MODE>
+static void launch_major(srb_mat *m, double *o0, double *o1, uint32_t *flags) {
+    srb_ctx *c = m->ctx;
+    const uint64_t n = m->nmajor();
+    if (n == 0) return;
+    const double avg = (double)m->st->nnz / (double)n;
+    const bool wide = avg >= 96.0;
+    const int lpr = wide ? 32 : 8;
+    const uint64_t groups_per_cta = 256 / lpr;
+    uint64_t grid = (n + groups_per_cta - 1) / groups_per_cta;
+    const uint64_t cap = (uint64_t)c->sm_count * 8 * 4;  // 8 resident CTAs/SM, 4 waves
+    if (grid > cap) grid = cap;
+    const int64_t *off = m->st->offsets->as<int64_t>();
+#define GO(VT, L) SRB_LAUNCH((major_reduce_kernel<VT, L, MODE>), (unsigned)grid, 256, 0, c->stream, off, m->values->as<VT>(), n, o0, o1, flags)
+    if (m->vdtype == SRB_F32) {
+        if (wide) GO(float, 32); else GO(float, 8);
+    } else {
+        if (wide) GO(double, 32); else GO(double, 8);
+    }
+#undef GO
+}
+
+void major_sum_absmax(srb_mat *m) {
+    if (m->has_pending()) materialize(m, false);
+    if (m->major.valid) return;
+    cudaStream_t st = m->ctx->stream;
+    const uint64_t n = m->nmajor();
+    m->major.sum = dev_zeros(st, sizeof(double) * (n + 1));
+    m->major.absmax = dev_zeros(st, sizeof(double) * (n + 1));
+    m->major.flags = dev_zeros(st, sizeof(uint32_t) * 2);
+    launch_major<MODE_SUM_ABSMAX>(m, m->major.sum->as<double>(), m->major.absmax->as<double>(),
+                                  m->major.flags->as<uint32_t>());
+    m->major.valid = true;
+}
+
+void major_variance(srb_mat *m, double *d_out) {
+    if (m->has_pending()) materialize(m, false);
+    launch_major<MODE_VARIANCE>(m, d_out, nullptr, nullptr);
+}
+
+void major_min_max(srb_mat *m, double *d_min, double *d_max) {
+    if (m->has_pending()) materialize(m, false);
+    launch_major<MODE_MINMAX>(m, d_min, d_max, nullptr);
+}
+
+}  // namespace srb

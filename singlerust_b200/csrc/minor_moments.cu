@@ -1,0 +1,615 @@
+// minor_moments.cu — K2/K3/K4: per-MINOR-line moments (per gene on CSR) and the deferred value transforms
+// (total-count scale, log1p), fused into one pass over the nnz.
+//
+// Replaces: helper/csr.rs Column branches (number 29-36, sum 94-100, variance 172-186) and helper/csc.rs Row
+// branches; scale/mod.rs:59-89,141-173 (value scaling) and transform/mod.rs:36-56 (log1p).
+//
+// Why fixed point: per-gene sums are a scatter-reduce into ~30 k bins. On sm_100a only 32-bit INTEGER
+// shared-memory atomics are native (ATOMS.ADD); f32/f64/u64 shared atomics compile to CAS spin loops and global
+// fp64 REDs run at <1 lane/clk/SM — both far from the HBM roofline. So every value is quantised once to
+// q = rint(v * 2^F) < 2^28 (F chosen on the device from the exact max |v|), and count / sum(q) / sum(q^2) are
+// accumulated EXACTLY in shared-memory integer limbs with carry propagation, flushed as 32-bit limbs into
+// 64-bit global accumulators (no carries needed there), and combined at the end. Integer addition is
+// associative, so the moments are bit-identical for any grid shape, any shard count and any GPU count.
+// Quantisation error: |v - q 2^-F| <= 2^-(F+1) <= max|v| * 2^-28 per value (for f32 data of similar magnitude
+// this is below the f32 ulp), unbiased; see DESIGN.md for the bound on the variance.
+//
+// Shared-memory bins: 4 words / gene  [sum_lo | sq_lo | sq_mid | packed(count:14, sum_hi:12, sq_hi:6)]
+// => 16 B/gene; genes are split into S column stripes so a stripe fits in <= ~160 KB; a CTA owns one
+// (row block, stripe) and reads only the contiguous part of each row that falls into its stripe (column
+// indices are sorted within a row; split points are found once per structure by binary search).
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace srb {
+
+static constexpr int kFusedThreads = 1024;
+static constexpr uint32_t kMaxRowsPerBlock = 8192;   // packed count field (14 bits) and carry fields
+static constexpr size_t kBinSmemBudget = 160 * 1024;  // per CTA
+static constexpr int kMaxStripes = 8;
+
+// ---------------------------------------------------------------------------------------------------
+// small helper kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void splits_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx, uint64_t nmajor,
+                              int S, uint32_t W, int64_t *__restrict__ splits) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = nmajor * (uint64_t)(S - 1);
+    if (t >= total) return;
+    const uint64_t r = t % nmajor;
+    const int s = (int)(t / nmajor);  // boundary between stripe s and s+1
+    const uint32_t bound = (uint32_t)(s + 1) * W;
+    int64_t lo = off[r], hi = off[r + 1];
+    while (lo < hi) {  // first k with idx[k] >= bound
+        const int64_t mid = (lo + hi) >> 1;
+        if (idx[mid] < bound) lo = mid + 1; else hi = mid;
+    }
+    splits[(uint64_t)s * nmajor + r] = lo;
+}
+
+// scale[i] = 0 if sum == 0 else target / sum   (scale/mod.rs:9-15, 93-99)
+__global__ void line_scale_kernel(const double *__restrict__ sum, uint64_t n, double target, double *__restrict__ scale) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) scale[i] = (sum[i] == 0.0) ? 0.0 : target / sum[i];
+}
+
+// out[0] = max_i a[i] * |b[i]| (b may be null => 1). Non-negative doubles order like their bit patterns.
+__global__ void max_prod_kernel(const double *__restrict__ a, const double *__restrict__ b, uint64_t n,
+                                unsigned long long *__restrict__ out) {
+    double mx = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double v = fabs(a[i]) * (b ? fabs(b[i]) : 1.0);
+        if (v == v) mx = fmax(mx, v);
+        else mx = INFINITY;  // NaN => unbounded
+    }
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+}
+__global__ void mul_scalar_kernel(double *a, const double *b) { a[0] = a[0] * b[0]; }
+
+// F such that rint(bound' * 2^F) < 2^28, bound' = bound (or log1p(bound)) with a safety margin
+__global__ void fexp_kernel(const double *__restrict__ bound, int do_log1p, int *__restrict__ fexp) {
+    double b = bound[0];
+    if (do_log1p) b = log1p(b);
+    b *= 1.0 + 1e-6;
+    int e = 0;
+    if (b > 0.0 && isfinite(b)) e = ilogb(b) + 1;  // b < 2^e
+    int F = 28 - e;
+    if (F > 100) F = 100;
+    if (F < -900) F = -900;
+    fexp[0] = F;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// value transform shared by all kernels: x = v * scale ; optional log1p. COMPACT (float) and FAITHFUL (double)
+// ---------------------------------------------------------------------------------------------------
+template <typename VTO>
+struct Xform;
+template <>
+struct Xform<float> {
+    // f32 pipeline: the scale is rounded once to f32 (rel 6e-8), log1pf is <= 1 ulp
+    template <typename VTI>
+    static __device__ __forceinline__ float apply(VTI v, double sc, bool has_scale, bool lg) {
+        float x = (float)v;
+        if (has_scale) x *= (float)sc;
+        if (lg) x = log1pf(x);
+        return x;
+    }
+};
+template <>
+struct Xform<double> {
+    // reference arithmetic: (v as f64) * scale, f64::ln_1p  (scale/mod.rs:66-72, transform/mod.rs:38-41)
+    template <typename VTI>
+    static __device__ __forceinline__ double apply(VTI v, double sc, bool has_scale, bool lg) {
+        double x = (double)v;
+        if (has_scale) x *= sc;
+        if (lg) x = log1p(x);
+        return x;
+    }
+};
+
+struct FusedParams {
+    const int64_t *off;
+    const uint32_t *idx;
+    const void *vin;
+    void *vout;
+    const double *scale;  // null => none
+    int scale_major;
+    int do_log1p;
+    const int64_t *splits;
+    int S;
+    uint32_t W;
+    uint64_t nmajor, nminor;
+    uint32_t rows_per_block;
+    const int *fexp;
+    unsigned long long *acc;  // 6 * nminor: cnt, sumA, sumB, sqA, sqB, sqC
+    unsigned long long *absmax_bits;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// (A) fused exact kernel
+// ---------------------------------------------------------------------------------------------------
+template <typename VTI, typename VTO, bool WRITE>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const FusedParams p) {
+    extern __shared__ uint32_t bins[];
+    const uint32_t W = p.W;
+    uint32_t *s_sum = bins, *s_sqlo = bins + W, *s_sqmid = bins + 2 * (size_t)W, *s_pack = bins + 3 * (size_t)W;
+    for (uint32_t i = threadIdx.x; i < 4 * W; i += kFusedThreads) bins[i] = 0;
+    __syncthreads();
+
+    const int s = (int)(blockIdx.x % (unsigned)p.S);
+    const uint64_t rb = blockIdx.x / (unsigned)p.S;
+    const uint32_t col_lo = (uint32_t)s * W;
+    const uint64_t r0 = rb * p.rows_per_block;
+    const uint64_t r1 = min(r0 + (uint64_t)p.rows_per_block, p.nmajor);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int F = p.fexp[0];
+    const double qs = ldexp(1.0, F);
+    const float qsf = (float)qs;
+    const VTI *vin = reinterpret_cast<const VTI *>(p.vin);
+    VTO *vout = reinterpret_cast<VTO *>(p.vout);  // may alias vin (in-place): same thread, same element
+
+    const bool has_scale = p.scale != nullptr;
+    const bool lg = p.do_log1p != 0;
+    VTO local_max = 0;
+
+    for (uint64_t r = r0 + warp; r < r1; r += kFusedThreads / 32) {
+        const int64_t a = (s == 0) ? p.off[r] : p.splits[(uint64_t)(s - 1) * p.nmajor + r];
+        const int64_t b = (s == p.S - 1) ? p.off[r + 1] : p.splits[(uint64_t)s * p.nmajor + r];
+        const double sc_row = (has_scale && p.scale_major) ? p.scale[r] : 1.0;
+#pragma unroll 4
+        for (int64_t k = a + lane; k < b; k += 32) {
+            const uint32_t c = p.idx[k];
+            const VTI v = vin[k];
+            const double sc = (has_scale && !p.scale_major) ? p.scale[c] : sc_row;
+            const VTO x = Xform<VTO>::apply(v, sc, has_scale, lg);
+            if (WRITE) vout[k] = x;
+            local_max = x > local_max ? x : local_max;
+            uint32_t q;
+            if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
+            else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
+            const uint32_t g = c - col_lo;
+            const uint32_t o1 = atomicAdd(&s_sum[g], q);
+            const uint32_t c1 = (uint32_t)((o1 + q) < o1);
+            const unsigned long long q2 = (unsigned long long)q * q;
+            const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
+            const uint32_t o2 = atomicAdd(&s_sqlo[g], l);
+            const uint32_t add3 = h + (uint32_t)((o2 + l) < o2);
+            const uint32_t o3 = atomicAdd(&s_sqmid[g], add3);
+            const uint32_t c3 = (uint32_t)((o3 + add3) < o3);
+            atomicAdd(&s_pack[g], (1u << 18) | (c1 << 6) | c3);
+        }
+    }
+    __syncthreads();
+    unsigned long long *acc = p.acc;
+    const uint64_t M = p.nminor;
+    for (uint32_t g = threadIdx.x; g < W; g += kFusedThreads) {
+        const uint32_t pk = s_pack[g];
+        const uint32_t cnt = pk >> 18;
+        if (cnt == 0) continue;
+        const uint64_t col = (uint64_t)col_lo + g;
+        atomicAdd(&acc[col], (unsigned long long)cnt);
+        atomicAdd(&acc[M + col], (unsigned long long)s_sum[g]);
+        const uint32_t sh = (pk >> 6) & 0xFFFu;
+        if (sh) atomicAdd(&acc[2 * M + col], (unsigned long long)sh);
+        atomicAdd(&acc[3 * M + col], (unsigned long long)s_sqlo[g]);
+        atomicAdd(&acc[4 * M + col], (unsigned long long)s_sqmid[g]);
+        const uint32_t qh = pk & 63u;
+        if (qh) atomicAdd(&acc[5 * M + col], (unsigned long long)qh);
+    }
+    double lm = warp_max((double)local_max);
+    if (lane == 0 && lm > 0.0) atomicMax(p.absmax_bits, (unsigned long long)__double_as_longlong(lm));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (B) transform only (no moments): one warp per line, pure streaming
+// ---------------------------------------------------------------------------------------------------
+template <typename VTI, typename VTO>
+__global__ void __launch_bounds__(256) transform_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
+                                                        const VTI *__restrict__ vin, VTO *__restrict__ vout,
+                                                        const double *__restrict__ scale, int scale_major,
+                                                        int do_log1p, uint64_t nmajor) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    const bool has_scale = scale != nullptr;
+    for (uint64_t r = warp; r < nmajor; r += nwarps) {
+        const int64_t a = off[r], b = off[r + 1];
+        const double sc_row = (has_scale && scale_major) ? scale[r] : 1.0;
+#pragma unroll 4
+        for (int64_t k = a + lane; k < b; k += 32) {
+            const double sc = (has_scale && !scale_major) ? scale[idx[k]] : sc_row;
+            vout[k] = Xform<VTO>::apply(vin[k], sc, has_scale, do_log1p != 0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// (C) general moments (negative / non-finite data, or too many minor lines for stripes): fp64 global REDs
+// ---------------------------------------------------------------------------------------------------
+template <typename VT>
+__global__ void __launch_bounds__(256) moments_general_kernel(const int64_t *__restrict__ off,
+                                                              const uint32_t *__restrict__ idx,
+                                                              const VT *__restrict__ val, uint64_t nmajor,
+                                                              double *__restrict__ cnt, double *__restrict__ sum,
+                                                              double *__restrict__ sq) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    for (uint64_t r = warp; r < nmajor; r += nwarps) {
+        const int64_t a = off[r], b = off[r + 1];
+        for (int64_t k = a + lane; k < b; k += 32) {
+            const uint32_t c = idx[k];
+            const double v = (double)val[k];
+            atomicAdd(&cnt[c], 1.0);
+            atomicAdd(&sum[c], v);
+            atomicAdd(&sq[c], v * v);
+        }
+    }
+}
+
+// exact accumulators -> doubles. sum = (sumA + sumB 2^32) 2^-F ; sq = (sqA + sqB 2^32 + sqC 2^64) 2^-2F
+__global__ void finalize_exact_kernel(const unsigned long long *__restrict__ acc, uint64_t M, const int *__restrict__ fexp,
+                                      double *__restrict__ cnt, double *__restrict__ sum, double *__restrict__ sq) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const int F = fexp[0];
+    cnt[j] = (double)acc[j];
+    const double s = (double)acc[2 * M + j] * 4294967296.0 + (double)acc[M + j];
+    // exact 128-bit recombination of the three limbs, then one rounding to double
+    unsigned __int128 t = (unsigned __int128)acc[3 * M + j] + ((unsigned __int128)acc[4 * M + j] << 32) +
+                          ((unsigned __int128)acc[5 * M + j] << 64);
+    const unsigned long long thi = (unsigned long long)(t >> 64), tlo = (unsigned long long)t;
+    const double q = (double)thi * 18446744073709551616.0 + (double)tlo;
+    sum[j] = ldexp(s, -F);
+    sq[j] = ldexp(q, -2 * F);
+}
+
+// variance_whole_helper minor branch (csr.rs:179-184): count>0 ? sq/cnt - mean^2 : 0.0
+__global__ void minor_variance_kernel(const double *__restrict__ cnt, const double *__restrict__ sum,
+                                      const double *__restrict__ sq, uint64_t M, int sqrt_it, double *__restrict__ out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    double r = 0.0;
+    if (cnt[j] > 0.0) {
+        const double mean = sum[j] / cnt[j];
+        r = sq[j] / cnt[j] - mean * mean;
+    }
+    out[j] = sqrt_it ? sqrt(r) : r;
+}
+
+template <typename VT>
+__global__ void __launch_bounds__(256) minor_minmax_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
+                                                           const VT *__restrict__ val, uint64_t nnz,
+                                                           unsigned long long *__restrict__ kmin,
+                                                           unsigned long long *__restrict__ kmax) {
+    for (uint64_t k = (uint64_t)blockIdx.x * 256 + threadIdx.x; k < nnz; k += (uint64_t)gridDim.x * 256) {
+        const double v = (double)val[k];
+        if (v != v) continue;  // f64::min/max ignore NaN operands
+        const unsigned long long key = f64_to_ordered(v);
+        const uint32_t c = idx[k];
+        if (key < kmin[c]) atomicMin(&kmin[c], key);
+        if (key > kmax[c]) atomicMax(&kmax[c], key);
+    }
+}
+__global__ void minmax_init_kernel(unsigned long long *kmin, unsigned long long *kmax, uint64_t M) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    kmin[j] = f64_to_ordered(INFINITY);
+    kmax[j] = f64_to_ordered(-INFINITY);
+}
+__global__ void minmax_decode_kernel(const unsigned long long *kmin, const unsigned long long *kmax, uint64_t M,
+                                     double *mn, double *mx) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    mn[j] = ordered_to_f64(kmin[j]);
+    mx[j] = ordered_to_f64(kmax[j]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static inline unsigned blocks_for(uint64_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+static void ensure_splits(srb_mat *m, int S, uint32_t W) {
+    Structure &st = *m->st;
+    if (S <= 1) return;
+    if (st.nstripes == S && st.splits) return;
+    cudaStream_t s = m->ctx->stream;
+    st.splits = dev_alloc(s, sizeof(int64_t) * st.nmajor * (size_t)(S - 1));
+    const uint64_t total = st.nmajor * (uint64_t)(S - 1);
+    SRB_LAUNCH(splits_kernel, blocks_for(total, 256), 256, 0, s, st.offsets->as<int64_t>(), st.indices->as<uint32_t>(),
+               st.nmajor, S, W, st.splits->as<int64_t>());
+    st.nstripes = S;
+}
+
+static void stripe_plan(const srb_mat *m, int *S, uint32_t *W) {
+    const uint64_t M = m->nminor();
+    const uint64_t per = kBinSmemBudget / 16;  // genes per stripe at most
+    int s = (int)((M + per - 1) / per);
+    if (s < 1) s = 1;
+    uint32_t w = (uint32_t)((M + s - 1) / s);
+    w = (w + 31u) & ~31u;
+    *S = s;
+    *W = w;
+}
+
+// Decide whether the exact fixed-point path applies: values must be finite and non-negative (count matrices and
+// their normalised / log1p'd forms always are) and the stripe count moderate.
+static bool exact_path_ok(srb_mat *m) {
+    int S;
+    uint32_t W;
+    stripe_plan(m, &S, &W);
+    if (S > kMaxStripes) return false;
+    uint32_t flags[2];
+    SRB_CUDA(cudaMemcpyAsync(flags, m->major.flags->as<uint32_t>(), sizeof(flags), cudaMemcpyDeviceToHost, m->ctx->stream));
+    SRB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    if (flags[0] || flags[1]) return false;
+    if (m->pend_scale) {
+        // a negative or non-finite scale can only come from a negative/non-finite line sum
+        // (scale = target/sum): covered by the flags for major sums; for minor sums the sums of
+        // non-negative finite values are non-negative finite. target < 0 flips the sign:
+        // handled by the caller (normalize with target < 0 disables the exact path via pend_bound = inf).
+    }
+    return true;
+}
+
+template <typename VTI, typename VTO>
+static void launch_fused(srb_mat *m, const FusedParams &p, bool write, unsigned grid, size_t smem) {
+    cudaStream_t s = m->ctx->stream;
+    if (write) {
+        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, true>), grid, kFusedThreads, smem, s, p);
+    } else {
+        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, false>), grid, kFusedThreads, smem, s, p);
+    }
+}
+
+// Apply the pending transforms; when want_moments, also produce the per-minor-line moments of the result.
+void materialize(srb_mat *m, bool want_moments) {
+    srb_ctx *c = m->ctx;
+    cudaStream_t s = c->stream;
+    const bool pending = m->has_pending();
+    if (!pending && (!want_moments || m->minor.valid)) return;
+    Structure &st = *m->st;
+    const uint64_t M = st.nminor, N = st.nmajor, nnz = st.nnz;
+
+    // output storage type: FAITHFUL promotes to f64 whenever a transform is applied (reference behaviour)
+    int out_dtype = m->vdtype;
+    if (pending && c->value_mode == SRB_VALUES_FAITHFUL && (m->pend_scale || m->src_dtype != SRB_F32)) out_dtype = SRB_F64;
+
+    // the bound of the values whose moments are taken
+    Buf bound;
+    if (want_moments) {
+        if (pending) {
+            bound = m->pend_bound;
+        } else {
+            if (!m->absmax_all) {
+                major_sum_absmax(m);
+                m->absmax_all = dev_zeros(s, sizeof(double));
+                SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), (const double *)nullptr, N,
+                           m->absmax_all->as<unsigned long long>());
+            }
+            bound = m->absmax_all;
+        }
+    }
+    bool exact = false;
+    if (want_moments) {
+        // major.flags describe the stored values; pending transforms with a finite bound keep them valid
+        if (!m->major.valid && !pending) major_sum_absmax(m);
+        exact = m->major.valid ? exact_path_ok(m) : false;
+        if (exact && pending) {
+            double b;
+            SRB_CUDA(cudaMemcpyAsync(&b, bound->as<double>(), sizeof(double), cudaMemcpyDeviceToHost, s));
+            SRB_CUDA(cudaStreamSynchronize(s));
+            if (!(b >= 0.0) || !std::isfinite(b)) exact = false;
+        }
+    }
+
+    Buf new_values = m->values;
+    const bool need_new_buffer = pending && (out_dtype != m->vdtype || m->values.use_count() > 1);
+    if (need_new_buffer) new_values = dev_alloc(s, (out_dtype == SRB_F32 ? 4 : 8) * (nnz ? nnz : 1));
+
+    MinorMoments mm;
+    Buf new_absmax;
+    if (exact) {
+        int S;
+        uint32_t W;
+        stripe_plan(m, &S, &W);
+        ensure_splits(m, S, W);
+        mm.exact_path = true;
+        mm.acc = dev_zeros(s, sizeof(unsigned long long) * 6 * (M ? M : 1));
+        mm.fexp = dev_alloc(s, sizeof(int));
+        new_absmax = dev_zeros(s, sizeof(double));
+        SRB_LAUNCH(fexp_kernel, 1, 1, 0, s, bound->as<double>(), (int)(pending && m->pend_log1p), mm.fexp->as<int>());
+        FusedParams p;
+        p.off = st.offsets->as<int64_t>();
+        p.idx = st.indices->as<uint32_t>();
+        p.vin = m->values->p;
+        p.vout = new_values->p;
+        p.scale = m->pend_scale ? m->pend_scale->as<double>() : nullptr;
+        p.scale_major = m->pend_scale_major ? 1 : 0;
+        p.do_log1p = m->pend_log1p ? 1 : 0;
+        p.splits = S > 1 ? st.splits->as<int64_t>() : nullptr;
+        p.S = S;
+        p.W = W;
+        p.nmajor = N;
+        p.nminor = M;
+        uint64_t rpb = (N + (uint64_t)c->sm_count * 2 - 1) / ((uint64_t)c->sm_count * 2);
+        if (rpb < 32) rpb = 32;
+        if (rpb > kMaxRowsPerBlock) rpb = kMaxRowsPerBlock;
+        p.rows_per_block = (uint32_t)rpb;
+        p.fexp = mm.fexp->as<int>();
+        p.acc = mm.acc->as<unsigned long long>();
+        p.absmax_bits = new_absmax->as<unsigned long long>();
+        const uint64_t nb = (N + rpb - 1) / rpb;
+        const unsigned grid = (unsigned)(nb * (uint64_t)S);
+        const size_t smem = (size_t)W * 16;
+        if (grid > 0) {
+            StageTimer t(c, ST_FUSED);
+            const bool in32 = m->vdtype == SRB_F32, out32 = out_dtype == SRB_F32;
+            if (in32 && out32) launch_fused<float, float>(m, p, pending, grid, smem);
+            else if (in32 && !out32) launch_fused<float, double>(m, p, pending, grid, smem);
+            else if (!in32 && !out32) launch_fused<double, double>(m, p, pending, grid, smem);
+            else throw Error(SRB_ERR_INVALID_ARG, "f64 -> f32 demotion is never requested");
+        }
+        mm.cnt = dev_alloc(s, sizeof(double) * (M ? M : 1));
+        mm.sum = dev_alloc(s, sizeof(double) * (M ? M : 1));
+        mm.sq = dev_alloc(s, sizeof(double) * (M ? M : 1));
+        if (c->nranks > 1 && m->format == SRB_CSR) {
+            StageTimer t(c, ST_ALLREDUCE);
+            allreduce_u64_sum(c, mm.acc->as<uint64_t>(), 6 * M);
+            mm.reduced = true;
+        }
+        if (M) SRB_LAUNCH(finalize_exact_kernel, blocks_for(M, 256), 256, 0, s, mm.acc->as<unsigned long long>(), M,
+                          mm.fexp->as<int>(), mm.cnt->as<double>(), mm.sum->as<double>(), mm.sq->as<double>());
+        mm.valid = true;
+    } else {
+        if (pending && nnz) {
+            StageTimer t(c, ST_FUSED);
+            const unsigned grid = (unsigned)std::min<uint64_t>((N + 7) / 8, (uint64_t)c->sm_count * 32);
+            const double *sc = m->pend_scale ? m->pend_scale->as<double>() : nullptr;
+            const int sm = m->pend_scale_major ? 1 : 0, lg = m->pend_log1p ? 1 : 0;
+            const int64_t *off = st.offsets->as<int64_t>();
+            const uint32_t *idx = st.indices->as<uint32_t>();
+            if (m->vdtype == SRB_F32 && out_dtype == SRB_F32)
+                SRB_LAUNCH((transform_kernel<float, float>), grid, 256, 0, s, off, idx, m->values->as<float>(), new_values->as<float>(), sc, sm, lg, N);
+            else if (m->vdtype == SRB_F32)
+                SRB_LAUNCH((transform_kernel<float, double>), grid, 256, 0, s, off, idx, m->values->as<float>(), new_values->as<double>(), sc, sm, lg, N);
+            else
+                SRB_LAUNCH((transform_kernel<double, double>), grid, 256, 0, s, off, idx, m->values->as<double>(), new_values->as<double>(), sc, sm, lg, N);
+        }
+        if (want_moments) {
+            mm.exact_path = false;
+            mm.cnt = dev_zeros(s, sizeof(double) * (M ? M : 1));
+            mm.sum = dev_zeros(s, sizeof(double) * (M ? M : 1));
+            mm.sq = dev_zeros(s, sizeof(double) * (M ? M : 1));
+            if (nnz) {
+                const unsigned grid = (unsigned)std::min<uint64_t>((N + 7) / 8, (uint64_t)c->sm_count * 32);
+                const int64_t *off = st.offsets->as<int64_t>();
+                const uint32_t *idx = st.indices->as<uint32_t>();
+                if (out_dtype == SRB_F32)
+                    SRB_LAUNCH((moments_general_kernel<float>), grid, 256, 0, s, off, idx, new_values->as<float>(), N, mm.cnt->as<double>(), mm.sum->as<double>(), mm.sq->as<double>());
+                else
+                    SRB_LAUNCH((moments_general_kernel<double>), grid, 256, 0, s, off, idx, new_values->as<double>(), N, mm.cnt->as<double>(), mm.sum->as<double>(), mm.sq->as<double>());
+            }
+            if (c->nranks > 1 && m->format == SRB_CSR) {
+                StageTimer t(c, ST_ALLREDUCE);
+                allreduce_f64_sum(c, mm.cnt->as<double>(), M);
+                allreduce_f64_sum(c, mm.sum->as<double>(), M);
+                allreduce_f64_sum(c, mm.sq->as<double>(), M);
+                mm.reduced = true;
+            }
+            mm.valid = true;
+        }
+    }
+
+    if (pending) {
+        m->values = new_values;
+        m->vdtype = out_dtype;
+        m->pend_scale.reset();
+        m->pend_log1p = false;
+        m->pend_bound.reset();
+        m->major = MajorStats();
+        m->absmax_all = new_absmax;  // exact path measured it; otherwise unknown (null)
+        m->minor = MinorMoments();
+    }
+    if (want_moments) m->minor = mm;
+}
+
+void ensure_minor_moments(srb_mat *m) {
+    if (m->minor.valid && !m->has_pending()) return;
+    materialize(m, true);
+}
+
+void minor_variance_from_moments(srb_mat *m, double *d_out, bool sqrt_it) {
+    ensure_minor_moments(m);
+    const uint64_t M = m->nminor();
+    if (M) SRB_LAUNCH(minor_variance_kernel, blocks_for(M, 256), 256, 0, m->ctx->stream, m->minor.cnt->as<double>(),
+                      m->minor.sum->as<double>(), m->minor.sq->as<double>(), M, sqrt_it ? 1 : 0, d_out);
+}
+
+void minor_min_max(srb_mat *m, double *d_min, double *d_max) {
+    if (m->has_pending()) materialize(m, false);
+    srb_ctx *c = m->ctx;
+    cudaStream_t s = c->stream;
+    const uint64_t M = m->nminor(), nnz = m->st->nnz;
+    if (!M) return;
+    Buf keys = dev_alloc(s, sizeof(unsigned long long) * 2 * M);
+    unsigned long long *kmin = keys->as<unsigned long long>(), *kmax = kmin + M;
+    SRB_LAUNCH(minmax_init_kernel, blocks_for(M, 256), 256, 0, s, kmin, kmax, M);
+    if (nnz) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((nnz + 255) / 256, (uint64_t)c->sm_count * 16);
+        if (m->vdtype == SRB_F32)
+            SRB_LAUNCH((minor_minmax_kernel<float>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), nnz, kmin, kmax);
+        else
+            SRB_LAUNCH((minor_minmax_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), nnz, kmin, kmax);
+    }
+    SRB_LAUNCH(minmax_decode_kernel, blocks_for(M, 256), 256, 0, s, kmin, kmax, M, d_min, d_max);
+    if (c->nranks > 1 && m->format == SRB_CSR) {
+        allreduce_f64_min(c, d_min, M);
+        allreduce_f64_max(c, d_max, M);
+    }
+}
+
+// ---- normalisation bookkeeping (called from api.cu) --------------------------------------------------
+void set_pending_normalize(srb_mat *m, double target, int direction) {
+    srb_ctx *c = m->ctx;
+    cudaStream_t s = c->stream;
+    if (m->has_pending()) materialize(m, false);  // sums must be those of the current logical values
+    const bool major = m->dir_is_major(direction);
+    const uint64_t n = major ? m->nmajor() : m->nminor();
+    Buf scale = dev_alloc(s, sizeof(double) * (n ? n : 1));
+    Buf bound = dev_zeros(s, sizeof(double));
+    {
+        StageTimer t(c, ST_ROWSUM);
+        major_sum_absmax(m);
+    }
+    if (major) {
+        if (n) SRB_LAUNCH(line_scale_kernel, blocks_for(n, 256), 256, 0, s, m->major.sum->as<double>(), n, target, scale->as<double>());
+        if (n) SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), scale->as<double>(), n, bound->as<unsigned long long>());
+    } else {
+        ensure_minor_moments(m);
+        // on a sharded CSR the minor sums are already global (allreduced); scale is replicated
+        if (n) SRB_LAUNCH(line_scale_kernel, blocks_for(n, 256), 256, 0, s, m->minor.sum->as<double>(), n, target, scale->as<double>());
+        Buf smax = dev_zeros(s, sizeof(double));
+        if (n) SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, scale->as<double>(), (const double *)nullptr, n, smax->as<unsigned long long>());
+        if (!m->absmax_all) {
+            m->absmax_all = dev_zeros(s, sizeof(double));
+            SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), (const double *)nullptr, m->nmajor(), m->absmax_all->as<unsigned long long>());
+        }
+        SRB_CUDA(cudaMemcpyAsync(bound->p, m->absmax_all->p, sizeof(double), cudaMemcpyDeviceToDevice, s));
+        SRB_LAUNCH(mul_scalar_kernel, 1, 1, 0, s, bound->as<double>(), smax->as<double>());
+    }
+    if (!(target >= 0.0)) {
+        const double inf = INFINITY;  // negative target flips signs: exact (non-negative) path not applicable
+        SRB_CUDA(cudaMemcpyAsync(bound->p, &inf, sizeof(double), cudaMemcpyHostToDevice, s));
+        SRB_CUDA(cudaStreamSynchronize(s));
+    }
+    m->pend_scale = scale;
+    m->pend_scale_major = major;
+    m->pend_bound = bound;
+    // caches describe the pre-transform values from now on: keep major (needed for flags) but drop minor
+    m->minor = MinorMoments();
+}
+
+void set_pending_log1p(srb_mat *m) {
+    cudaStream_t s = m->ctx->stream;
+    if (m->pend_log1p) materialize(m, false);  // log1p(log1p(x)): apply the first one now
+    if (!m->pend_scale) {
+        // bound of the stored values
+        major_sum_absmax(m);
+        if (!m->absmax_all) {
+            m->absmax_all = dev_zeros(s, sizeof(double));
+            SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), (const double *)nullptr, m->nmajor(), m->absmax_all->as<unsigned long long>());
+        }
+        m->pend_bound = m->absmax_all;
+    }
+    m->pend_log1p = true;
+    m->minor = MinorMoments();
+}
+
+}  // namespace srb

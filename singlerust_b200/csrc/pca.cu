@@ -1,0 +1,364 @@
+// pca.cu — K6..K9: PCA on the selected (HVG) columns. Replaces pca_inplace, src/memory/processing/dim_red/mod.rs:24-94
+// (select -> convert_to_array_f64_selected (shared/mod.rs:230-259) -> PCABuilder.fit/transform) with a Gram
+// formulation that never builds the n x d f64 block the reference allocates (16 GB at 1M x 2000):
+//
+//   X  : n x d block of the (normalised, log1p'd) selected columns, held as split-fp16 panels Xh + Xl (22-bit
+//        mantissa, |x - (xh+xl)| <= 2^-22 |x|), row-major [n][dpad]
+//   G  = X^T X                        (d x d, tensor cores or fp64 CUDA cores; allreduced over row shards)
+//   mu = sum_j / n, sigma^2 = sumsq_j / n - mu^2   from the per-gene moments already computed (ddof = 0, ALL cells)
+//   C  = D^-1 (G - n mu mu^T) D^-1    = Z^T Z with Z = (X - mu)/sigma      (pca/mod.rs:87-111 semantics)
+//   C  = V L V^T (symmetric eig);  components = V[:, :k];  ratio = L[:k] / trace(C)   (pca/mod.rs:131-151)
+//   scores = Z V_k = X (D^-1 V_k) - mu^T D^-1 V_k                          (pca/mod.rs:156-185)
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace srb {
+
+static unsigned nb(uint64_t n, unsigned t = 256) { return (unsigned)std::max<uint64_t>(1, (n + t - 1) / t); }
+
+// lut[col] = position in the selection, -1 if not selected; duplicates: the LAST position wins (HashMap insert
+// order, shared/mod.rs:241)
+__global__ void lut_fill_kernel(int *lut, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lut[i] = -1;
+}
+__global__ void lut_set_kernel(int *lut, const uint32_t *sel, uint64_t n_sel) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_sel) atomicMax(&lut[sel[j]], (int)j);
+}
+
+// reference-shaped dense block (parity/debug): all rows [row0,row0+nrows) x selection, f64 row-major
+template <typename VT>
+__global__ void __launch_bounds__(256) densify_f64_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
+                                                          const VT *__restrict__ val, const int *__restrict__ lut,
+                                                          uint64_t row0, uint64_t nrows, uint64_t n_sel, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    for (uint64_t r = warp; r < nrows; r += nwarps) {
+        const int64_t a = off[row0 + r], b = off[row0 + r + 1];
+        for (int64_t k = a + lane; k < b; k += 32) {
+            const int p = lut[idx[k]];
+            if (p >= 0) out[r * n_sel + (uint64_t)p] = (double)val[k];
+        }
+    }
+}
+
+void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, double *d_out, uint64_t row0, uint64_t nrows) {
+    if (m->has_pending()) materialize(m, false);
+    cudaStream_t s = m->ctx->stream;
+    const uint64_t M = m->nminor();
+    Buf lut = dev_alloc(s, 4 * (M + 1));
+    SRB_LAUNCH(lut_fill_kernel, nb(M), 256, 0, s, lut->as<int>(), M);
+    SRB_LAUNCH(lut_set_kernel, nb(n_sel), 256, 0, s, lut->as<int>(), d_sel, n_sel);
+    SRB_CUDA(cudaMemsetAsync(d_out, 0, 8 * nrows * n_sel, s));
+    const unsigned grid = (unsigned)std::min<uint64_t>((nrows + 7) / 8, (uint64_t)m->ctx->sm_count * 32);
+    if (m->vdtype == SRB_F32)
+        SRB_LAUNCH((densify_f64_kernel<float>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut->as<int>(), row0, nrows, n_sel, d_out);
+    else
+        SRB_LAUNCH((densify_f64_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), row0, nrows, n_sel, d_out);
+}
+
+// K6: CSR rows -> split-fp16 panels. One warp per row builds the dpad-wide row in shared memory (zero fill,
+// scatter the selected entries), then writes it out with 16-byte coalesced stores. HBM: 8 B/nnz in, 4*dpad B/row out.
+template <typename VT>
+__global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
+                                                             const VT *__restrict__ val, const int *__restrict__ lut,
+                                                             uint64_t nrows, uint32_t dpad, __half *__restrict__ Xh,
+                                                             __half *__restrict__ Xl) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __half *rh = reinterpret_cast<__half *>(smem_raw) + (size_t)w * 2 * dpad;
+    __half *rl = rh + dpad;
+    const uint64_t warp = (uint64_t)blockIdx.x * 8 + w;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    const uint32_t nvec = dpad / 8;  // uint4 = 8 halves
+    for (uint64_t r = warp; r < nrows; r += nwarps) {
+        uint4 *zh = reinterpret_cast<uint4 *>(rh), *zl = reinterpret_cast<uint4 *>(rl);
+        for (uint32_t i = lane; i < nvec; i += 32) zh[i] = make_uint4(0, 0, 0, 0), zl[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        const int64_t a = off[r], b = off[r + 1];
+        for (int64_t k = a + lane; k < b; k += 32) {
+            const int p = lut[idx[k]];
+            if (p >= 0) {
+                const float x = (float)val[k];  // values are f32-representable in COMPACT mode; f64 values keep 22 bits
+                const __half h = __float2half_rn(x);
+                const float rem = (float)((double)val[k] - (double)__half2float(h));
+                rh[p] = h;
+                rl[p] = __float2half_rn(rem);
+            }
+        }
+        __syncwarp();
+        uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
+        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = zh[i], ol[i] = zl[i];
+        __syncwarp();
+    }
+}
+
+// K7 (validation path): G += X^T X in fp64 on CUDA cores. 64x64 output tile per CTA, upper-triangular tiles only,
+// split over row ranges (fp64 REDs into G). x = (double)xh + (double)xl.
+static constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(256) gram_f64_kernel(const __half *__restrict__ Xh, const __half *__restrict__ Xl,
+                                                       uint64_t nrows, uint32_t dpad, uint64_t rows_per_split,
+                                                       double *__restrict__ G) {
+    // decode upper-triangular tile (ti <= tj)
+    const uint32_t nt = dpad / GT;
+    uint32_t t = blockIdx.x, ti = 0;
+    while (t >= nt - ti) t -= nt - ti, ++ti;
+    const uint32_t tj = ti + t;
+    const uint64_t r0 = (uint64_t)blockIdx.y * rows_per_split;
+    const uint64_t r1 = min(r0 + rows_per_split, nrows);
+    __shared__ double As[GK][GT + 1], Bs[GK][GT + 1];
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    double acc[4][4] = {};
+    for (uint64_t rk = r0; rk < r1; rk += GK) {
+        for (int e = threadIdx.x; e < GK * GT; e += 256) {
+            const int kk = e / GT, c = e % GT;
+            const uint64_t r = rk + kk;
+            double a = 0.0, b = 0.0;
+            if (r < r1) {
+                const uint64_t ia = r * dpad + (uint64_t)ti * GT + c, ib = r * dpad + (uint64_t)tj * GT + c;
+                a = (double)__half2float(Xh[ia]) + (double)__half2float(Xl[ia]);
+                b = (double)__half2float(Xh[ib]) + (double)__half2float(Xl[ib]);
+            }
+            As[kk][c] = a, Bs[kk][c] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i], bv[i] = Bs[kk][tx * 4 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t gi = ti * GT + ty * 4 + i, gj = tj * GT + tx * 4 + j;
+            if (acc[i][j] != 0.0) atomicAdd(&G[(uint64_t)gi * dpad + gj], acc[i][j]);
+        }
+}
+// copy the upper triangle (tile-wise computed: entries with tile(i) <= tile(j)) onto the lower one
+__global__ void gram_mirror_kernel(double *G, uint32_t dpad, uint32_t tile) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (uint64_t)dpad * dpad) return;
+    const uint32_t i = (uint32_t)(e / dpad), j = (uint32_t)(e % dpad);
+    if (i / tile > j / tile) G[e] = G[(uint64_t)j * dpad + i];
+}
+
+// per selected gene: mean over ALL cells and 1/std (ddof 0) from the global per-gene moments
+__global__ void sel_stats_kernel(const uint32_t *__restrict__ sel, uint64_t n_sel, const double *__restrict__ sum,
+                                 const double *__restrict__ sq, double n_cells, int center, int scale,
+                                 double *__restrict__ mu, double *__restrict__ inv_sd, uint32_t *__restrict__ flag) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_sel) return;
+    const uint32_t g = sel[j];
+    const double mean = sum[g] / n_cells;
+    double var = sq[g] / n_cells - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double sd = sqrt(var);
+    mu[j] = (center || scale) ? mean : 0.0;  // pca/mod.rs:87-119: mean is stored whenever center||scale
+    double is = 1.0;
+    if (scale) {
+        if (sd > 0.0) is = 1.0 / sd;
+        else { is = 0.0; atomicOr(flag, 1u); }  // the reference divides by zero here (NaN columns)
+    }
+    inv_sd[j] = is;
+}
+// C[i][j] = (G[i][j] - center * n mu_i mu_j) * is_i * is_j    (compact n_sel x n_sel, symmetric)
+__global__ void corr_kernel(const double *__restrict__ G, uint32_t dpad, uint64_t n_sel, const double *__restrict__ mu,
+                            const double *__restrict__ inv_sd, double n_cells, int center, double *__restrict__ C) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_sel * n_sel) return;
+    const uint64_t i = e / n_sel, j = e % n_sel;
+    double g = G[i * dpad + j];
+    if (center) g -= n_cells * mu[i] * mu[j];
+    C[e] = g * inv_sd[i] * inv_sd[j];
+}
+__global__ void trace_kernel(const double *__restrict__ C, uint64_t n_sel, double *__restrict__ out) {
+    double s = 0.0;
+    for (uint64_t i = threadIdx.x; i < n_sel; i += blockDim.x) s += C[i * n_sel + i];
+    s = warp_sum(s);
+    __shared__ double part[32];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) t += part[w];
+        out[0] = t;
+    }
+}
+// eigenvectors come back column-major with ascending eigenvalues: column (n_sel-1-c) is component c.
+// Sign convention: the entry of largest magnitude of every component is positive (deterministic across runs).
+// comps[j][c] (row-major n_sel x k), W[p][c] = inv_sd[p] * comps[p][c] (row-major dpad x kpad, zero padded),
+// bias[c] = sum_p mu[p] W[p][c], evr[c] = lambda_c / trace
+__global__ void components_kernel(const double *__restrict__ evec, const double *__restrict__ evals_asc, uint64_t n_sel,
+                                  uint32_t k, uint32_t kpad, const double *__restrict__ mu, const double *__restrict__ inv_sd,
+                                  int center, const double *__restrict__ trace, double *__restrict__ comps,
+                                  double *__restrict__ W, double *__restrict__ bias, double *__restrict__ evr) {
+    const uint32_t c = blockIdx.x;
+    if (c >= k) return;
+    const double *v = evec + (n_sel - 1 - c) * n_sel;
+    __shared__ double s_val[256];
+    __shared__ int s_idx[256];
+    double best = -1.0;
+    int bi = 0;
+    for (uint64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
+        const double a = fabs(v[j]);
+        if (a > best) best = a, bi = (int)j;
+    }
+    s_val[threadIdx.x] = best, s_idx[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double ob = s_val[threadIdx.x + o];
+            const int oi = s_idx[threadIdx.x + o];
+            if (ob > s_val[threadIdx.x] || (ob == s_val[threadIdx.x] && oi < s_idx[threadIdx.x])) s_val[threadIdx.x] = ob, s_idx[threadIdx.x] = oi;
+        }
+        __syncthreads();
+    }
+    const double sgn = v[s_idx[0]] < 0.0 ? -1.0 : 1.0;
+    __syncthreads();
+    double b = 0.0;
+    for (uint64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
+        const double x = sgn * v[j];
+        comps[j * k + c] = x;
+        const double w = x * inv_sd[j];
+        W[j * kpad + c] = w;
+        b += mu[j] * w;
+    }
+    b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) s_val[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (unsigned w = 0; w < blockDim.x / 32; ++w) t += s_val[w];
+        bias[c] = center ? t : 0.0;
+        evr[c] = evals_asc[n_sel - 1 - c] / trace[0];
+    }
+}
+
+// K9 (validation path): scores[r][c] = sum_p x[r][p] W[p][c] - bias[c]. One warp per row; the 32 lanes load 32
+// consecutive panel entries, ballot the non-zeros and broadcast each to all lanes; lane l owns components l, l+32.
+__global__ void __launch_bounds__(256) scores_simt_kernel(const __half *__restrict__ Xh, const __half *__restrict__ Xl,
+                                                          uint64_t nrows, uint32_t dpad, const double *__restrict__ W,
+                                                          uint32_t kpad, const double *__restrict__ bias, uint32_t k,
+                                                          uint32_t c0, double *__restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    for (uint64_t r = warp; r < nrows; r += nwarps) {
+        double a0 = 0.0, a1 = 0.0;
+        const __half *xh = Xh + r * dpad, *xl = Xl + r * dpad;
+        for (uint32_t p0 = 0; p0 < dpad; p0 += 32) {
+            const double x = (double)__half2float(xh[p0 + lane]) + (double)__half2float(xl[p0 + lane]);
+            unsigned mask = __ballot_sync(0xffffffffu, x != 0.0);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double xv = __shfl_sync(0xffffffffu, x, src);
+                const double *wr = W + (uint64_t)(p0 + src) * kpad + c0;
+                a0 += xv * wr[lane];
+                a1 += xv * wr[lane + 32];
+            }
+        }
+        if (c0 + lane < k) scores[r * k + c0 + lane] = a0 - bias[c0 + lane];
+        if (c0 + lane + 32 < k) scores[r * k + c0 + lane + 32] = a1 - bias[c0 + lane + 32];
+    }
+}
+
+void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool center, bool scale, int gram_mode,
+             PcaOut out) {
+    srb_ctx *c = m->ctx;
+    cudaStream_t s = c->stream;
+    SRB_REQUIRE(gram_mode == 0 || gram_mode == 1, SRB_ERR_INVALID_ARG, "gram_mode must be 0 (tcgen05) or 1 (fp64)");
+    const uint64_t n = m->nrows, M = m->nminor();
+    const double n_cells = (double)(c->nranks > 1 ? m->global_nrows : m->nrows);
+    SRB_REQUIRE(n_cells >= 2, SRB_ERR_INVALID_ARG, "PCA needs at least two cells");
+    ensure_minor_moments(m);  // also applies pending transforms (fused)
+
+    const uint32_t dpad = (uint32_t)((n_sel + 255) / 256 * 256);
+    const uint32_t kpad = (uint32_t)((k + 63) / 64 * 64);
+    Buf lut = dev_alloc(s, 4 * (M + 1));
+    SRB_LAUNCH(lut_fill_kernel, nb(M), 256, 0, s, lut->as<int>(), M);
+    SRB_LAUNCH(lut_set_kernel, nb(n_sel), 256, 0, s, lut->as<int>(), d_sel, n_sel);
+
+    Buf flag = dev_zeros(s, 4);
+    Buf mu = dev_alloc(s, 8 * dpad), inv_sd = dev_alloc(s, 8 * dpad);
+    SRB_LAUNCH(sel_stats_kernel, nb(n_sel), 256, 0, s, d_sel, n_sel, m->minor.sum->as<double>(), m->minor.sq->as<double>(),
+               n_cells, center ? 1 : 0, scale ? 1 : 0, mu->as<double>(), inv_sd->as<double>(), flag->as<uint32_t>());
+
+    // K6 panels
+    Buf Xh = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad), Xl = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad);
+    if (n) {
+        StageTimer t(c, ST_DENSIFY);
+        const size_t smem = (size_t)8 * 2 * dpad * sizeof(__half);
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 16);
+        if (m->vdtype == SRB_F32) {
+            SRB_CUDA(cudaFuncSetAttribute(densify_panels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut->as<int>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        } else {
+            SRB_CUDA(cudaFuncSetAttribute(densify_panels_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        }
+    }
+    // K7 Gram
+    Buf G = dev_zeros(s, 8 * (size_t)dpad * dpad);
+    {
+        StageTimer t(c, ST_GRAM);
+        if (gram_mode == 0) {
+            gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, G->as<double>());
+        } else if (n) {
+            const uint32_t nt = dpad / GT;
+            const uint32_t ntiles = nt * (nt + 1) / 2;
+            uint64_t splits = std::max<uint64_t>(1, std::min<uint64_t>((n + 511) / 512, (uint64_t)c->sm_count * 8 / ntiles + 1));
+            const uint64_t rps = ((n + splits - 1) / splits + GK - 1) / GK * GK;
+            splits = (n + rps - 1) / rps;
+            SRB_LAUNCH(gram_f64_kernel, dim3(ntiles, (unsigned)splits), 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, rps, G->as<double>());
+            SRB_LAUNCH(gram_mirror_kernel, nb((uint64_t)dpad * dpad), 256, 0, s, G->as<double>(), dpad, (uint32_t)GT);
+        }
+    }
+    if (c->nranks > 1) {
+        StageTimer t(c, ST_ALLREDUCE);
+        allreduce_f64_sum(c, G->as<double>(), (size_t)dpad * dpad);
+    }
+    // K8: correlation matrix + symmetric eigendecomposition
+    Buf C = dev_alloc(s, 8 * n_sel * n_sel), evals = dev_alloc(s, 8 * n_sel), tr = dev_alloc(s, 8);
+    Buf comps = dev_alloc(s, 8 * n_sel * k), W = dev_zeros(s, 8 * (size_t)dpad * kpad), bias = dev_zeros(s, 8 * kpad), evr = dev_alloc(s, 8 * k);
+    {
+        StageTimer t(c, ST_EIG);
+        SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, G->as<double>(), dpad, n_sel, mu->as<double>(), inv_sd->as<double>(), n_cells, center ? 1 : 0, C->as<double>());
+        SRB_LAUNCH(trace_kernel, 1, 256, 0, s, C->as<double>(), n_sel, tr->as<double>());
+        sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, evals->as<double>());
+        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), n_sel, (uint32_t)k, kpad, mu->as<double>(), inv_sd->as<double>(), center ? 1 : 0, tr->as<double>(), comps->as<double>(), W->as<double>(), bias->as<double>(), evr->as<double>());
+    }
+    // K9 scores
+    Buf scores = dev_alloc(s, 8 * std::max<uint64_t>(n, 1) * k);
+    if (n) {
+        StageTimer t(c, ST_SCORES);
+        if (gram_mode == 0) {
+            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), bias->as<double>(), (uint32_t)k, scores->as<double>());
+        } else {
+            const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 32);
+            for (uint32_t c0 = 0; c0 < k; c0 += 64)
+                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, bias->as<double>(), (uint32_t)k, c0, scores->as<double>());
+        }
+    }
+    if (out.scores && n) SRB_CUDA(cudaMemcpyAsync(out.scores, scores->p, 8 * n * k, cudaMemcpyDeviceToHost, s));
+    if (out.components) SRB_CUDA(cudaMemcpyAsync(out.components, comps->p, 8 * n_sel * k, cudaMemcpyDeviceToHost, s));
+    if (out.evr) SRB_CUDA(cudaMemcpyAsync(out.evr, evr->p, 8 * k, cudaMemcpyDeviceToHost, s));
+    uint32_t hflag = 0;
+    SRB_CUDA(cudaMemcpyAsync(&hflag, flag->p, 4, cudaMemcpyDeviceToHost, s));
+    SRB_CUDA(cudaStreamSynchronize(s));
+    SRB_REQUIRE(!hflag, SRB_ERR_NAN, "a selected feature has zero variance over all cells while scale=true (the reference divides by zero: NaN scores)");
+}
+
+}  // namespace srb
