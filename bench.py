@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json): cells/s through
+total-count normalise + log1p -> per-gene moments -> HVG(top 2000) -> 50-PC PCA on a synthetic
+1M-cell x 30k-gene CSR (5 % nnz) per GPU.
+
+  python bench.py --gpus N --steps K --warmup W          # our arm (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port), rank 0 only
+
+A "step" is one pass of the whole pipeline over one device-resident batch (the rank's row shard). Weak scaling:
+every rank holds `--cells` rows of one global matrix of N * cells rows; the per-gene moments and the Gram matrix
+are allreduced over NCCL inside the step. Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cells_per_sec_normalise_hvg_pca"
+UNIT = "cells/s"
+SEED = 0x5EED0002
+TARGET_SUM = 1e4
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=1_000_000, help="cells per GPU")
+    ap.add_argument("--genes", type=int, default=30_000)
+    ap.add_argument("--hvg", type=int, default=2000)
+    ap.add_argument("--pcs", type=int, default=50)
+    ap.add_argument("--gram-mode", type=int, default=int(os.environ.get("SRB_GRAM_MODE", "0")), help="0 tcgen05, 1 fp64 CUDA cores")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-cells", type=int, default=0, help="0 = auto")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md): nvidia-smi during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, mxc = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: take the nearest samples
+            sm = [float(l.split(",")[1]) for _, l in self.lines[-3:] if len(l.split(",")) >= 8]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (reference-faithful arithmetic, threaded where the loops allow) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def cpu_pipeline_once(sample, hvg, pcs):
+    """One pass of normalise + log1p + per-gene variance + HVG + selected densify + PCA on the CPU. Returns seconds."""
+    from oracle import oracle as O
+    from oracle import pca_oracle as P
+    t0 = time.perf_counter()
+    lm, _, _, _, gv = O.norm_log1p_genevar_omp(sample, TARGET_SUM)           # scale/mod.rs + transform/mod.rs + csr.rs:172-186
+    sel = O.select_hvg(gv, hvg)                                               # dim_red/mod.rs:135-140
+    dense = O.densify_selected(lm, np.arange(sample.nrows, dtype=np.uint64), sel)  # shared/mod.rs:230-259
+    P.pca_fit_transform(dense, min(pcs, len(sel)), True, True)                # PCABuilder.fit/transform (LAPACK, all cores)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(args, sample_cells, repeats=1):
+    from oracle import oracle as O
+    from singlerust_b200 import synth
+    thr, amp = synth.gene_tables(args.genes, seed=SEED, mean_density=0.05)
+    sample = O.synth_csr(SEED, sample_cells, args.genes, thr, amp)
+    times = [cpu_pipeline_once(sample, args.hvg, args.pcs) for _ in range(repeats)]
+    t = min(times)
+    return {"value": sample_cells / t, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": f"first {sample_cells} cells of the same synthetic matrix (seed 0x{SEED:X}), full pipeline, "
+                      f"{t:.2f} s; stats loops threaded with OpenMP, PCA = LAPACK gesdd via NumPy; the reference's own "
+                      f"stats loops are single-threaded (SURVEY F2)"}, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_total = args.steps + args.warmup
+    sample_cells = args.cpu_sample_cells or int(max(2048, min(16384, 120_000 // max(1, n_total))))
+    from oracle import oracle as O
+    from singlerust_b200 import synth
+    thr, amp = synth.gene_tables(args.genes, seed=SEED, mean_density=0.05)
+    sample = O.synth_csr(SEED, sample_cells, args.genes, thr, amp)
+    for _ in range(args.warmup):
+        cpu_pipeline_once(sample, args.hvg, args.pcs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pipeline_once(sample, args.hvg, args.pcs)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    v = sample_cells / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, sample_cells=sample_cells),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+                         "sample": f"{sample_cells} cells x {args.genes} genes per step (bounded sample of the workload)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust and cannot be built in this image (no cargo/rustc); this is the oracle port of its CPU path",
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, sample_cells=None):
+    return {"workload": "configs[2]: 1M cells x 30k genes CSR 5% nnz per GPU: normalise + log1p + HVG(top 2k) + 50-PC PCA",
+            "cells_per_gpu": args.cells if sample_cells is None else sample_cells, "genes": args.genes, "hvg": args.hvg,
+            "pcs": args.pcs, "target_sum": TARGET_SUM, "seed": f"0x{SEED:X}", "parallelism": f"row-shard x{args.gpus}",
+            "l2": "inputs (12 GB/GPU) are larger than L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from singlerust_b200 import _ffi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    ctx = _ffi.Context(local_rank)
+    if world > 1:
+        obj = [_ffi.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        ctx.comm_init(obj[0], rank, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    thr, amp = synth.gene_tables(args.genes, seed=SEED, mean_density=0.05)
+    mat = _ffi.DeviceMatrix.synth(ctx, SEED, args.cells, args.genes, thr, amp, row0=rank * args.cells)
+    mat.set_shard(rank * args.cells, world * args.cells)
+    info = mat.info()
+    nnz = info["nnz"]
+
+    def step():
+        work = mat.clone()  # copy-on-write: the fused kernel reads the raw counts and writes a fresh value buffer
+        work.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, want_outputs=False)
+        st = ctx.last_stage_ms()
+        work.free()
+        return st
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = _ffi.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record(stream)
+    stages = []
+    for _ in range(args.steps):
+        stages.append(step())
+    e1.record(stream)
+    barrier()
+    t_wall1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    launches = _ffi.kernel_launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * args.cells / (ms_step * 1e-3)
+
+    # ---- rooflines from the library's per-stage CUDA-event times (ctx stream), averaged over the timed steps ----
+    hbm, tf_burst, tf_sust, peak_src = measured_peaks()
+    mean_stage = {k: float(np.mean([s[k] for s in stages])) for k in stages[0]}
+    n, d = args.cells, min(args.hvg, args.genes)
+    dpad = (d + 255) // 256 * 256
+    alg = {
+        "row_sums": 4 * nnz + 8 * (n + 1),                       # K1: f32 values + offsets
+        "fused_norm_log1p_moments": 12 * nnz + 16 * n,            # K4: idx + val read, val write, offsets + scale
+        "densify": 8 * nnz + 8 * n + 4 * n * dpad,                # K6: idx + val read, split-fp16 panels written
+        "scores": 4 * n * dpad + 8 * n * args.pcs,                # K9: panels read, f64 scores written
+    }
+    roof = {}
+    for k, b in alg.items():
+        ms = mean_stage.get(k, 0.0)
+        if ms > 0:
+            a = b / (ms * 1e-3) / 1e9
+            roof[k] = {"bound": "hbm", "achieved": a, "peak": hbm, "unit": "GB/s", "frac": a / hbm, "traffic": None,
+                       "ms": ms, "algorithmic_bytes": b}
+    gms = mean_stage.get("gram", 0.0)
+    if gms > 0:
+        a = n * d * d / (gms * 1e-3) / 1e12  # SYRK algorithmic flops n*d^2
+        roof["gram"] = {"bound": "tensor", "achieved": a, "peak": tf_sust, "unit": "TFLOP/s", "frac": a / tf_sust,
+                        "traffic": None, "ms": gms, "algorithmic_flops": n * d * d,
+                        "executed_flops_note": "split-fp16 x3 on upper-triangular 256x256 tiles (see DESIGN.md)"}
+    dominant = max(roof, key=lambda k: roof[k]["ms"]) if roof else None
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 values / f64 accumulate (fp16x2-split tensor Gram)" if args.gram_mode == 0 else "f32 values / f64 accumulate",
+        "data": "synthetic", "config": workload_config(args), "gpu_launches": int(launches), "clocks": clocks,
+        "nnz_per_gpu": int(nnz), "stage_ms": mean_stage, "peaks": peak_src,
+        "roofline": dict(roof[dominant], kernel=dominant) if dominant else None,
+        "rooflines": roof,
+    }
+
+    # ---- e2e: through the C ABI with HOST buffers (pinned), H2D + pipeline + D2H of the scores, every step ----
+    if not args.no_e2e:
+        try:
+            line["e2e"] = run_e2e(args, ctx, mat, rank, world, dev, barrier)
+        except Exception as ex:  # never lose the main line
+            line["e2e"] = {"value": None, "unit": UNIT, "error": str(ex)[:300]}
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            sample = args.cpu_sample_cells or 16384
+            cb, _ = cpu_baseline(args, sample)
+            line["cpu_baseline"] = cb
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(ex)[:300]}
+    if rank == 0:
+        print(json.dumps(line))
+    mat.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, ctx, mat, rank, world, dev, barrier):
+    import psutil
+    import torch
+    import torch.distributed as dist
+    from singlerust_b200 import _ffi
+
+    info = mat.info()
+    n, nnz, k = info["nrows"], info["nnz"], min(args.pcs, args.hvg)
+    # host layout of the reference: usize (u64) offsets + indices, f32 values (nalgebra-sparse CsrMatrix<f32>)
+    need = 8 * (n + 1) + 12 * nnz + 8 * n * k
+    avail = psutil.virtual_memory().available / max(1, world)
+    if need * 1.3 > avail:
+        raise RuntimeError(f"host RAM too small for the e2e host copy: need {need/1e9:.1f} GB per rank, have {avail/1e9:.1f} GB")
+    off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+    idx = torch.empty(nnz, dtype=torch.int64).pin_memory()
+    val = torch.empty(nnz, dtype=torch.float32).pin_memory()
+    scores = torch.empty((n, k), dtype=torch.float64).pin_memory()
+    _ffi.check(_ffi.lib().srb_mat_download(mat._h, _ffi._ptr(off), _ffi._ptr(idx), None, _ffi._ptr(val)))
+
+    def step():
+        m = _ffi.DeviceMatrix.upload(ctx, _ffi.CSR, n, args.genes, off, idx, val, nnz=nnz, idx_width=8, dtype=_ffi.F32)
+        m.set_shard(rank * n, world * n)
+        m.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, scores_out=scores)
+        m.free()
+
+    step()  # warm-up (allocations, pinned-path page faults)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.e2e_steps):
+        step()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.e2e_steps
+    h2d = 8 * (n + 1) + 12 * nnz
+    d2h = 8 * n * k + 8 * min(args.hvg, args.genes) * (k + 1) + 8 * k
+    return {"value": world * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": ms, "steps": args.e2e_steps,
+            "host_layout": "u64 offsets + u64 indices + f32 values in pinned memory (the Rust usize layout)"}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,7 +130,8 @@ struct MajorStats {
     bool valid = false;
     Buf sum;     // f64[nmajor]
     Buf absmax;  // f64[nmajor]
-    Buf flags;   // u32[2]: [0] any negative, [1] any non-finite
+    Buf absmin;  // f64[nmajor]: min |v| over the non-zero stored values of the line (+inf if none)
+    Buf flags;   // u32[3]: [0] any negative, [1] any non-finite, [2] any non-integer
 };
 
 }  // namespace srb
@@ -147,11 +148,11 @@ struct srb_mat {
     srb::Buf pend_scale;  // f64[nmajor] or f64[nminor]
     bool pend_scale_major = true;
     bool pend_log1p = false;
-    srb::Buf pend_bound;  // f64[1] device: upper bound of |value| after the pending transforms
+    srb::Buf pend_bound;  // f64[2] device: {upper bound of |value|, lower bound of the non-zero |value|} after scaling (before log1p)
     // caches of the CURRENT (post-pending) logical values; dropped on mutation
     srb::MajorStats major;
     srb::MinorMoments minor;
-    srb::Buf absmax_all;  // f64[1] device: max |v| of the materialised values (valid iff non-null)
+    srb::Buf absmax_all;  // f64[2] device: {max |v|, min non-zero |v|} of the materialised values (valid iff non-null)
     // sharding
     uint64_t global_row0 = 0, global_nrows = 0;
 

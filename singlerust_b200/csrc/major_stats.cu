@@ -33,7 +33,8 @@ __device__ __forceinline__ double group_min(double v) {
 template <typename VT, int LPR, int MODE>
 __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__restrict__ off, const VT *__restrict__ val,
                                                            uint64_t nmajor, double *__restrict__ o0,
-                                                           double *__restrict__ o1, uint32_t *__restrict__ flags) {
+                                                           double *__restrict__ o1, double *__restrict__ o2,
+                                                           uint32_t *__restrict__ flags) {
     const int lane = threadIdx.x % LPR;
     const uint64_t group = ((uint64_t)blockIdx.x * 256 + threadIdx.x) / LPR;
     const uint64_t ngroups = (uint64_t)gridDim.x * 256 / LPR;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
         const int64_t a = act ? off[i] : 0;
         const int64_t b = act ? off[i + 1] : 0;
         if (MODE == MODE_SUM_ABSMAX || MODE == MODE_VARIANCE) {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mx = 0;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0, mx = 0, mnz = INFINITY;
             int64_t k = a + lane;
             for (; k + 3 * LPR < b; k += 4 * LPR) {
                 const double v0 = (double)val[k], v1 = (double)val[k + LPR], v2 = (double)val[k + 2 * LPR],
@@ -53,8 +54,10 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
                 s0 += v0, s1 += v1, s2 += v2, s3 += v3;
                 if (MODE == MODE_SUM_ABSMAX) {
                     mx = fmax(fmax(mx, fabs(v0)), fmax(fabs(v1), fmax(fabs(v2), fabs(v3))));
+                    mnz = fmin(fmin(mnz, v0 != 0 ? fabs(v0) : INFINITY), fmin(v1 != 0 ? fabs(v1) : INFINITY, fmin(v2 != 0 ? fabs(v2) : INFINITY, v3 != 0 ? fabs(v3) : INFINITY)));
                     bad |= (v0 < 0) | (v1 < 0) | (v2 < 0) | (v3 < 0);
                     bad |= 2u * (!isfinite(v0) | !isfinite(v1) | !isfinite(v2) | !isfinite(v3));
+                    bad |= 4u * ((v0 != rint(v0)) | (v1 != rint(v1)) | (v2 != rint(v2)) | (v3 != rint(v3)));
                 }
             }
             for (; k < b; k += LPR) {
@@ -62,15 +65,18 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
                 s0 += v0;
                 if (MODE == MODE_SUM_ABSMAX) {
                     mx = fmax(mx, fabs(v0));
-                    bad |= (v0 < 0) | (2u * !isfinite(v0));
+                    mnz = fmin(mnz, v0 != 0 ? fabs(v0) : INFINITY);
+                    bad |= (v0 < 0) | (2u * !isfinite(v0)) | (4u * (v0 != rint(v0)));
                 }
             }
             const double sum = group_sum<LPR>((s0 + s1) + (s2 + s3));
             if (MODE == MODE_SUM_ABSMAX) {
                 mx = group_max<LPR>(mx);
+                mnz = group_min<LPR>(mnz);
                 if (act && lane == 0) {
                     o0[i] = sum;
                     o1[i] = mx;
+                    o2[i] = mnz;
                 }
             } else {
                 // variance_whole_helper major branch: mean = sum/count; sum((v-mean)^2)/count; 0/0 -> NaN
@@ -102,11 +108,15 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
             }
         }
     }
-    if (MODE == MODE_SUM_ABSMAX && bad) atomicOr(flags, bad & 1u), atomicOr(flags + 1, (bad >> 1) & 1u);
+    if (MODE == MODE_SUM_ABSMAX && bad) {
+        if (bad & 1u) atomicOr(flags, 1u);
+        if (bad & 2u) atomicOr(flags + 1, 1u);
+        if (bad & 4u) atomicOr(flags + 2, 1u);
+    }
 }
 
 template <int MODE>
-static void launch_major(srb_mat *m, double *o0, double *o1, uint32_t *flags) {
+static void launch_major(srb_mat *m, double *o0, double *o1, double *o2, uint32_t *flags) {
     srb_ctx *c = m->ctx;
     const uint64_t n = m->nmajor();
     if (n == 0) return;
@@ -118,7 +128,7 @@ static void launch_major(srb_mat *m, double *o0, double *o1, uint32_t *flags) {
     const uint64_t cap = (uint64_t)c->sm_count * 8 * 4;  // 8 resident CTAs/SM, 4 waves
     if (grid > cap) grid = cap;
     const int64_t *off = m->st->offsets->as<int64_t>();
-#define GO(VT, L) SRB_LAUNCH((major_reduce_kernel<VT, L, MODE>), (unsigned)grid, 256, 0, c->stream, off, m->values->as<VT>(), n, o0, o1, flags)
+#define GO(VT, L) SRB_LAUNCH((major_reduce_kernel<VT, L, MODE>), (unsigned)grid, 256, 0, c->stream, off, m->values->as<VT>(), n, o0, o1, o2, flags)
     if (m->vdtype == SRB_F32) {
         if (wide) GO(float, 32); else GO(float, 8);
     } else {
@@ -134,20 +144,21 @@ void major_sum_absmax(srb_mat *m) {
     const uint64_t n = m->nmajor();
     m->major.sum = dev_zeros(st, sizeof(double) * (n + 1));
     m->major.absmax = dev_zeros(st, sizeof(double) * (n + 1));
-    m->major.flags = dev_zeros(st, sizeof(uint32_t) * 2);
-    launch_major<MODE_SUM_ABSMAX>(m, m->major.sum->as<double>(), m->major.absmax->as<double>(),
+    m->major.absmin = dev_zeros(st, sizeof(double) * (n + 1));
+    m->major.flags = dev_zeros(st, sizeof(uint32_t) * 4);
+    launch_major<MODE_SUM_ABSMAX>(m, m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(),
                                   m->major.flags->as<uint32_t>());
     m->major.valid = true;
 }
 
 void major_variance(srb_mat *m, double *d_out) {
     if (m->has_pending()) materialize(m, false);
-    launch_major<MODE_VARIANCE>(m, d_out, nullptr, nullptr);
+    launch_major<MODE_VARIANCE>(m, d_out, nullptr, nullptr, nullptr);
 }
 
 void major_min_max(srb_mat *m, double *d_min, double *d_max) {
     if (m->has_pending()) materialize(m, false);
-    launch_major<MODE_MINMAX>(m, d_min, d_max, nullptr);
+    launch_major<MODE_MINMAX>(m, d_min, d_max, nullptr, nullptr);
 }
 
 }  // namespace srb

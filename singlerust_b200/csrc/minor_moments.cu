@@ -55,19 +55,32 @@ __global__ void line_scale_kernel(const double *__restrict__ sum, uint64_t n, do
     if (i < n) scale[i] = (sum[i] == 0.0) ? 0.0 : target / sum[i];
 }
 
-// out[0] = max_i a[i] * |b[i]| (b may be null => 1). Non-negative doubles order like their bit patterns.
-__global__ void max_prod_kernel(const double *__restrict__ a, const double *__restrict__ b, uint64_t n,
-                                unsigned long long *__restrict__ out) {
-    double mx = 0.0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const double v = fabs(a[i]) * (b ? fabs(b[i]) : 1.0);
-        if (v == v) mx = fmax(mx, v);
-        else mx = INFINITY;  // NaN => unbounded
-    }
-    mx = warp_max(mx);
-    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(mx));
+// range[0] = max_i amax[i]*|b[i]| ; range[1] = min_i amin[i]*|b[i]| over the strictly positive products (b null => 1).
+// Non-negative doubles order like their bit patterns, so integer atomics do the reduction.
+__global__ void range_init_kernel(unsigned long long *range) {
+    range[0] = 0ULL;
+    range[1] = 0x7FF0000000000000ULL;  // +inf
 }
-__global__ void mul_scalar_kernel(double *a, const double *b) { a[0] = a[0] * b[0]; }
+__global__ void range_prod_kernel(const double *__restrict__ amax, const double *__restrict__ amin,
+                                  const double *__restrict__ b, uint64_t n, unsigned long long *__restrict__ range) {
+    double mx = 0.0, mn = INFINITY;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double sc = b ? fabs(b[i]) : 1.0;
+        const double hi = fabs(amax[i]) * sc, lo = fabs(amin[i]) * sc;
+        if (hi == hi) mx = fmax(mx, hi);
+        else mx = INFINITY;  // NaN => unbounded
+        if (lo > 0.0) mn = fmin(mn, lo);
+    }
+    mx = warp_max(mx), mn = warp_min(mn);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(range, (unsigned long long)__double_as_longlong(mx));
+        atomicMin(range + 1, (unsigned long long)__double_as_longlong(mn));
+    }
+}
+__global__ void range_mul_kernel(double *out, const double *a, const double *b) {
+    out[0] = a[0] * b[0];
+    out[1] = a[1] * b[1];
+}
 
 // F such that rint(bound' * 2^F) < 2^28, bound' = bound (or log1p(bound)) with a safety margin
 __global__ void fexp_kernel(const double *__restrict__ bound, int do_log1p, int *__restrict__ fexp) {
@@ -125,7 +138,7 @@ struct FusedParams {
     uint32_t rows_per_block;
     const int *fexp;
     unsigned long long *acc;  // 6 * nminor: cnt, sumA, sumB, sqA, sqB, sqC
-    unsigned long long *absmax_bits;
+    unsigned long long *range_bits;  // [0] max, [1] min positive of the produced values
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -153,7 +166,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
 
     const bool has_scale = p.scale != nullptr;
     const bool lg = p.do_log1p != 0;
-    VTO local_max = 0;
+    VTO local_max = 0, local_min = INFINITY;
 
     for (uint64_t r = r0 + warp; r < r1; r += kFusedThreads / 32) {
         const int64_t a = (s == 0) ? p.off[r] : p.splits[(uint64_t)(s - 1) * p.nmajor + r];
@@ -167,6 +180,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
             const VTO x = Xform<VTO>::apply(v, sc, has_scale, lg);
             if (WRITE) vout[k] = x;
             local_max = x > local_max ? x : local_max;
+            local_min = (x > 0 && x < local_min) ? x : local_min;
             uint32_t q;
             if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
             else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
@@ -199,8 +213,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
         const uint32_t qh = pk & 63u;
         if (qh) atomicAdd(&acc[5 * M + col], (unsigned long long)qh);
     }
-    double lm = warp_max((double)local_max);
-    if (lane == 0 && lm > 0.0) atomicMax(p.absmax_bits, (unsigned long long)__double_as_longlong(lm));
+    const double lm = warp_max((double)local_max), ln = warp_min((double)local_min);
+    if (lane == 0) {
+        if (lm > 0.0) atomicMax(p.range_bits, (unsigned long long)__double_as_longlong(lm));
+        if (ln < INFINITY) atomicMin(p.range_bits + 1, (unsigned long long)__double_as_longlong(ln));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -280,6 +297,27 @@ __global__ void minor_variance_kernel(const double *__restrict__ cnt, const doub
     out[j] = sqrt_it ? sqrt(r) : r;
 }
 
+// Exact-path variance: the integer identity  cnt*sum(q^2) - (sum q)^2 >= 0  is evaluated in 128-bit integers, so
+// there is NO cancellation error at all (the reference's f64 one-pass form sq/cnt - mean^2, csr.rs:179-184, loses
+// ~eps*E[x^2]/var); a gene whose stored values are all equal gets exactly 0.0 like the reference.
+__global__ void minor_variance_exact_kernel(const unsigned long long *__restrict__ acc, uint64_t M, const int *__restrict__ fexp,
+                                            int sqrt_it, double *__restrict__ out) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    const unsigned long long cnt = acc[j];
+    double r = 0.0;
+    if (cnt > 0) {
+        const unsigned __int128 S = (unsigned __int128)acc[M + j] + ((unsigned __int128)acc[2 * M + j] << 32);
+        const unsigned __int128 Q = (unsigned __int128)acc[3 * M + j] + ((unsigned __int128)acc[4 * M + j] << 32) +
+                                    ((unsigned __int128)acc[5 * M + j] << 64);
+        const unsigned __int128 a = (unsigned __int128)cnt * Q, b = S * S;
+        const unsigned __int128 N = a >= b ? a - b : 0;
+        const double nd = (double)(unsigned long long)(N >> 64) * 18446744073709551616.0 + (double)(unsigned long long)N;
+        r = ldexp(nd / ((double)cnt * (double)cnt), -2 * fexp[0]);
+    }
+    out[j] = sqrt_it ? sqrt(r) : r;
+}
+
 template <typename VT>
 __global__ void __launch_bounds__(256) minor_minmax_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                            const VT *__restrict__ val, uint64_t nnz,
@@ -336,24 +374,47 @@ static void stripe_plan(const srb_mat *m, int *S, uint32_t *W) {
     *W = w;
 }
 
-// Decide whether the exact fixed-point path applies: values must be finite and non-negative (count matrices and
-// their normalised / log1p'd forms always are) and the stripe count moderate.
-static bool exact_path_ok(srb_mat *m) {
+static Buf new_range(cudaStream_t s) {
+    Buf r = dev_alloc(s, 2 * sizeof(double));
+    SRB_LAUNCH(range_init_kernel, 1, 1, 0, s, r->as<unsigned long long>());
+    return r;
+}
+// {max |v|, min non-zero |v|} of the stored values
+static void ensure_range_all(srb_mat *m) {
+    if (m->absmax_all) return;
+    major_sum_absmax(m);
+    cudaStream_t s = m->ctx->stream;
+    m->absmax_all = new_range(s);
+    if (m->nmajor())
+        SRB_LAUNCH(range_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), m->major.absmin->as<double>(),
+                   (const double *)nullptr, m->nmajor(), m->absmax_all->as<unsigned long long>());
+}
+
+// Decide whether the exact fixed-point path applies (one small D2H + sync):
+//  * stored values finite and non-negative (count matrices and their normalised / log1p'd forms always are)
+//  * moderate stripe count
+//  * quantisation keeps every value to <= 2^-17 relative: either integer-valued data below 2^28 (exact), or a
+//    dynamic range max/min <= 4096 of the values whose moments are taken
+//  * FAITHFUL f64 storage asks for the reference's f64 accumulation instead
+static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, int out_dtype) {
     int S;
     uint32_t W;
     stripe_plan(m, &S, &W);
     if (S > kMaxStripes) return false;
-    uint32_t flags[2];
-    SRB_CUDA(cudaMemcpyAsync(flags, m->major.flags->as<uint32_t>(), sizeof(flags), cudaMemcpyDeviceToHost, m->ctx->stream));
-    SRB_CUDA(cudaStreamSynchronize(m->ctx->stream));
+    if (m->ctx->value_mode == SRB_VALUES_FAITHFUL && out_dtype == SRB_F64) return false;
+    uint32_t flags[3];
+    double rng[2];
+    cudaStream_t s = m->ctx->stream;
+    SRB_CUDA(cudaMemcpyAsync(flags, m->major.flags->as<uint32_t>(), sizeof(flags), cudaMemcpyDeviceToHost, s));
+    SRB_CUDA(cudaMemcpyAsync(rng, range->p, sizeof(rng), cudaMemcpyDeviceToHost, s));
+    SRB_CUDA(cudaStreamSynchronize(s));
     if (flags[0] || flags[1]) return false;
-    if (m->pend_scale) {
-        // a negative or non-finite scale can only come from a negative/non-finite line sum
-        // (scale = target/sum): covered by the flags for major sums; for minor sums the sums of
-        // non-negative finite values are non-negative finite. target < 0 flips the sign:
-        // handled by the caller (normalize with target < 0 disables the exact path via pend_bound = inf).
-    }
-    return true;
+    double hi = rng[0], lo = rng[1];
+    if (!(hi >= 0.0) || !std::isfinite(hi)) return false;
+    if (lg) hi = std::log1p(hi), lo = std::log1p(lo);
+    if (!pending && !flags[2] && hi < 268435456.0) return true;  // integers: exactly representable
+    if (hi == 0.0 || std::isinf(lo)) return true;                // all zeros
+    return lo > 0.0 && hi / lo <= 4096.0;
 }
 
 template <typename VTI, typename VTO>
@@ -381,32 +442,17 @@ void materialize(srb_mat *m, bool want_moments) {
     int out_dtype = m->vdtype;
     if (pending && c->value_mode == SRB_VALUES_FAITHFUL && (m->pend_scale || m->src_dtype != SRB_F32)) out_dtype = SRB_F64;
 
-    // the bound of the values whose moments are taken
+    // the range of the values whose moments are taken
     Buf bound;
-    if (want_moments) {
-        if (pending) {
-            bound = m->pend_bound;
-        } else {
-            if (!m->absmax_all) {
-                major_sum_absmax(m);
-                m->absmax_all = dev_zeros(s, sizeof(double));
-                SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), (const double *)nullptr, N,
-                           m->absmax_all->as<unsigned long long>());
-            }
-            bound = m->absmax_all;
-        }
-    }
     bool exact = false;
     if (want_moments) {
-        // major.flags describe the stored values; pending transforms with a finite bound keep them valid
-        if (!m->major.valid && !pending) major_sum_absmax(m);
-        exact = m->major.valid ? exact_path_ok(m) : false;
-        if (exact && pending) {
-            double b;
-            SRB_CUDA(cudaMemcpyAsync(&b, bound->as<double>(), sizeof(double), cudaMemcpyDeviceToHost, s));
-            SRB_CUDA(cudaStreamSynchronize(s));
-            if (!(b >= 0.0) || !std::isfinite(b)) exact = false;
+        if (pending) {
+            bound = m->pend_bound;  // set_pending_* computed it together with major stats
+        } else {
+            ensure_range_all(m);
+            bound = m->absmax_all;
         }
+        exact = m->major.valid && exact_path_ok(m, bound, pending, pending && m->pend_log1p, out_dtype);
     }
 
     Buf new_values = m->values;
@@ -423,7 +469,7 @@ void materialize(srb_mat *m, bool want_moments) {
         mm.exact_path = true;
         mm.acc = dev_zeros(s, sizeof(unsigned long long) * 6 * (M ? M : 1));
         mm.fexp = dev_alloc(s, sizeof(int));
-        new_absmax = dev_zeros(s, sizeof(double));
+        new_absmax = new_range(s);
         SRB_LAUNCH(fexp_kernel, 1, 1, 0, s, bound->as<double>(), (int)(pending && m->pend_log1p), mm.fexp->as<int>());
         FusedParams p;
         p.off = st.offsets->as<int64_t>();
@@ -444,7 +490,7 @@ void materialize(srb_mat *m, bool want_moments) {
         p.rows_per_block = (uint32_t)rpb;
         p.fexp = mm.fexp->as<int>();
         p.acc = mm.acc->as<unsigned long long>();
-        p.absmax_bits = new_absmax->as<unsigned long long>();
+        p.range_bits = new_absmax->as<unsigned long long>();
         const uint64_t nb = (N + rpb - 1) / rpb;
         const unsigned grid = (unsigned)(nb * (uint64_t)S);
         const size_t smem = (size_t)W * 16;
@@ -528,8 +574,13 @@ void ensure_minor_moments(srb_mat *m) {
 void minor_variance_from_moments(srb_mat *m, double *d_out, bool sqrt_it) {
     ensure_minor_moments(m);
     const uint64_t M = m->nminor();
-    if (M) SRB_LAUNCH(minor_variance_kernel, blocks_for(M, 256), 256, 0, m->ctx->stream, m->minor.cnt->as<double>(),
-                      m->minor.sum->as<double>(), m->minor.sq->as<double>(), M, sqrt_it ? 1 : 0, d_out);
+    if (!M) return;
+    if (m->minor.exact_path)
+        SRB_LAUNCH(minor_variance_exact_kernel, blocks_for(M, 256), 256, 0, m->ctx->stream, m->minor.acc->as<unsigned long long>(), M,
+                   m->minor.fexp->as<int>(), sqrt_it ? 1 : 0, d_out);
+    else
+        SRB_LAUNCH(minor_variance_kernel, blocks_for(M, 256), 256, 0, m->ctx->stream, m->minor.cnt->as<double>(),
+                   m->minor.sum->as<double>(), m->minor.sq->as<double>(), M, sqrt_it ? 1 : 0, d_out);
 }
 
 void minor_min_max(srb_mat *m, double *d_min, double *d_max) {
@@ -563,30 +614,27 @@ void set_pending_normalize(srb_mat *m, double target, int direction) {
     const bool major = m->dir_is_major(direction);
     const uint64_t n = major ? m->nmajor() : m->nminor();
     Buf scale = dev_alloc(s, sizeof(double) * (n ? n : 1));
-    Buf bound = dev_zeros(s, sizeof(double));
+    Buf bound = new_range(s);
     {
         StageTimer t(c, ST_ROWSUM);
         major_sum_absmax(m);
     }
     if (major) {
         if (n) SRB_LAUNCH(line_scale_kernel, blocks_for(n, 256), 256, 0, s, m->major.sum->as<double>(), n, target, scale->as<double>());
-        if (n) SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), scale->as<double>(), n, bound->as<unsigned long long>());
+        if (n) SRB_LAUNCH(range_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), m->major.absmin->as<double>(), scale->as<double>(), n, bound->as<unsigned long long>());
     } else {
         ensure_minor_moments(m);
         // on a sharded CSR the minor sums are already global (allreduced); scale is replicated
         if (n) SRB_LAUNCH(line_scale_kernel, blocks_for(n, 256), 256, 0, s, m->minor.sum->as<double>(), n, target, scale->as<double>());
-        Buf smax = dev_zeros(s, sizeof(double));
-        if (n) SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, scale->as<double>(), (const double *)nullptr, n, smax->as<unsigned long long>());
-        if (!m->absmax_all) {
-            m->absmax_all = dev_zeros(s, sizeof(double));
-            SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), (const double *)nullptr, m->nmajor(), m->absmax_all->as<unsigned long long>());
-        }
-        SRB_CUDA(cudaMemcpyAsync(bound->p, m->absmax_all->p, sizeof(double), cudaMemcpyDeviceToDevice, s));
-        SRB_LAUNCH(mul_scalar_kernel, 1, 1, 0, s, bound->as<double>(), smax->as<double>());
+        Buf srange = new_range(s);
+        if (n) SRB_LAUNCH(range_prod_kernel, 64, 256, 0, s, scale->as<double>(), scale->as<double>(), (const double *)nullptr, n, srange->as<unsigned long long>());
+        ensure_range_all(m);
+        SRB_LAUNCH(range_mul_kernel, 1, 1, 0, s, bound->as<double>(), m->absmax_all->as<double>(), srange->as<double>());
     }
     if (!(target >= 0.0)) {
-        const double inf = INFINITY;  // negative target flips signs: exact (non-negative) path not applicable
-        SRB_CUDA(cudaMemcpyAsync(bound->p, &inf, sizeof(double), cudaMemcpyHostToDevice, s));
+        // a negative target flips signs: the exact (non-negative) path is not applicable
+        const double inf[2] = {INFINITY, 0.0};
+        SRB_CUDA(cudaMemcpyAsync(bound->p, inf, sizeof(inf), cudaMemcpyHostToDevice, s));
         SRB_CUDA(cudaStreamSynchronize(s));
     }
     m->pend_scale = scale;
@@ -597,15 +645,9 @@ void set_pending_normalize(srb_mat *m, double target, int direction) {
 }
 
 void set_pending_log1p(srb_mat *m) {
-    cudaStream_t s = m->ctx->stream;
     if (m->pend_log1p) materialize(m, false);  // log1p(log1p(x)): apply the first one now
     if (!m->pend_scale) {
-        // bound of the stored values
-        major_sum_absmax(m);
-        if (!m->absmax_all) {
-            m->absmax_all = dev_zeros(s, sizeof(double));
-            SRB_LAUNCH(max_prod_kernel, 64, 256, 0, s, m->major.absmax->as<double>(), (const double *)nullptr, m->nmajor(), m->absmax_all->as<unsigned long long>());
-        }
+        ensure_range_all(m);  // range of the stored values (also computes the major flags)
         m->pend_bound = m->absmax_all;
     }
     m->pend_log1p = true;
