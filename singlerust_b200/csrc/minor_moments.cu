@@ -291,8 +291,10 @@ __global__ void minor_variance_kernel(const double *__restrict__ cnt, const doub
     if (j >= M) return;
     double r = 0.0;
     if (cnt[j] > 0.0) {
+        // no FMA contraction: the reference (and the oracle) round mean*mean before the subtraction, which makes
+        // the variance of a constant line exactly 0.0 (HVG tie order depends on it)
         const double mean = sum[j] / cnt[j];
-        r = sq[j] / cnt[j] - mean * mean;
+        r = __dsub_rn(__ddiv_rn(sq[j], cnt[j]), __dmul_rn(mean, mean));
     }
     out[j] = sqrt_it ? sqrt(r) : r;
 }

@@ -2,13 +2,14 @@
 // (select -> convert_to_array_f64_selected (shared/mod.rs:230-259) -> PCABuilder.fit/transform) with a Gram
 // formulation that never builds the n x d f64 block the reference allocates (16 GB at 1M x 2000):
 //
-//   X  : n x d block of the (normalised, log1p'd) selected columns, held as split-fp16 panels Xh + Xl (22-bit
-//        mantissa, |x - (xh+xl)| <= 2^-22 |x|), row-major [n][dpad]
-//   G  = X^T X                        (d x d, tensor cores or fp64 CUDA cores; allreduced over row shards)
 //   mu = sum_j / n, sigma^2 = sumsq_j / n - mu^2   from the per-gene moments already computed (ddof = 0, ALL cells)
-//   C  = D^-1 (G - n mu mu^T) D^-1    = Z^T Z with Z = (X - mu)/sigma      (pca/mod.rs:87-111 semantics)
+//   Z  = (X - mu)/sigma : n x d block of the standardised selected columns (pca/mod.rs:87-111 semantics), held as
+//        split-fp16 panels Zh + Zl (22-bit mantissa, |z - (zh+zl)| <= 2^-22 |z|), row-major [n][dpad]. The block is
+//        centred BEFORE the Gram product: subtracting n mu mu^T afterwards would turn any accumulation bias of the
+//        tensor-core sums into a rank-one perturbation along mu/sigma ("why centre first").
+//   C  = Z^T Z                        (d x d, tensor cores or fp64 CUDA cores; allreduced over row shards)
 //   C  = V L V^T (symmetric eig);  components = V[:, :k];  ratio = L[:k] / trace(C)   (pca/mod.rs:131-151)
-//   scores = Z V_k = X (D^-1 V_k) - mu^T D^-1 V_k                          (pca/mod.rs:156-185)
+//   scores = Z V_k                                                          (pca/mod.rs:156-185)
 #include <algorithm>
 #include <cmath>
 
@@ -61,11 +62,14 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
         SRB_LAUNCH((densify_f64_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), row0, nrows, n_sel, d_out);
 }
 
-// K6: CSR rows -> split-fp16 panels. One warp per row builds the dpad-wide row in shared memory (zero fill,
-// scatter the selected entries), then writes it out with 16-byte coalesced stores. HBM: 8 B/nnz in, 4*dpad B/row out.
+// K6: CSR rows -> standardised split-fp16 panels. One warp per row builds the dpad-wide row in shared memory: every
+// column starts at the constant z of an implicit zero, (0 - shift_j) * inv_sd_j, then the stored entries are
+// scattered over it; the row is written out with 16-byte coalesced stores. HBM: 8 B/nnz in, 4*dpad B/row out.
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const int *__restrict__ lut,
+                                                             const float *__restrict__ shf, const float *__restrict__ isf,
+                                                             const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
                                                              uint64_t nrows, uint32_t dpad, __half *__restrict__ Xh,
                                                              __half *__restrict__ Xl) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -75,19 +79,20 @@ __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__re
     const uint64_t warp = (uint64_t)blockIdx.x * 8 + w;
     const uint64_t nwarps = (uint64_t)gridDim.x * 8;
     const uint32_t nvec = dpad / 8;  // uint4 = 8 halves
+    const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
     for (uint64_t r = warp; r < nrows; r += nwarps) {
         uint4 *zh = reinterpret_cast<uint4 *>(rh), *zl = reinterpret_cast<uint4 *>(rl);
-        for (uint32_t i = lane; i < nvec; i += 32) zh[i] = make_uint4(0, 0, 0, 0), zl[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = lane; i < nvec; i += 32) zh[i] = ch[i], zl[i] = cl[i];
         __syncwarp();
         const int64_t a = off[r], b = off[r + 1];
         for (int64_t k = a + lane; k < b; k += 32) {
             const int p = lut[idx[k]];
             if (p >= 0) {
-                const float x = (float)val[k];  // values are f32-representable in COMPACT mode; f64 values keep 22 bits
-                const __half h = __float2half_rn(x);
-                const float rem = (float)((double)val[k] - (double)__half2float(h));
+                // fp32 is enough here: the split keeps 22 bits of z, fp32 carries 24
+                const float z = ((float)val[k] - shf[p]) * isf[p];
+                const __half h = __float2half_rn(z);
                 rh[p] = h;
-                rl[p] = __float2half_rn(rem);
+                rl[p] = __float2half_rn(z - __half2float(h));
             }
         }
         __syncwarp();
@@ -154,34 +159,53 @@ __global__ void gram_mirror_kernel(double *G, uint32_t dpad, uint32_t tile) {
     if (i / tile > j / tile) G[e] = G[(uint64_t)j * dpad + i];
 }
 
-// per selected gene: mean over ALL cells and 1/std (ddof 0) from the global per-gene moments
-__global__ void sel_stats_kernel(const uint32_t *__restrict__ sel, uint64_t n_sel, const double *__restrict__ sum,
+// per selected gene: mean over ALL cells and 1/std (ddof 0) from the global per-gene moments; shift = mean when
+// centring; zc = split-fp16 of the standardised value of an implicit zero
+__global__ void sel_stats_kernel(const uint32_t *__restrict__ sel, uint64_t n_sel, uint32_t dpad, const double *__restrict__ sum,
                                  const double *__restrict__ sq, double n_cells, int center, int scale,
-                                 double *__restrict__ mu, double *__restrict__ inv_sd, uint32_t *__restrict__ flag) {
+                                 double *__restrict__ shift, double *__restrict__ inv_sd, float *__restrict__ shf,
+                                 float *__restrict__ isf, __half *__restrict__ zc_h, __half *__restrict__ zc_l,
+                                 uint32_t *__restrict__ flag) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_sel) return;
+    if (j >= dpad) return;
+    if (j >= n_sel) {
+        shift[j] = 0.0, inv_sd[j] = 0.0, shf[j] = 0.f, isf[j] = 0.f;
+        zc_h[j] = __float2half(0.f), zc_l[j] = __float2half(0.f);
+        return;
+    }
     const uint32_t g = sel[j];
     const double mean = sum[g] / n_cells;
-    double var = sq[g] / n_cells - mean * mean;
+    double var = __dsub_rn(__ddiv_rn(sq[g], n_cells), __dmul_rn(mean, mean));
     if (var < 0.0) var = 0.0;
     const double sd = sqrt(var);
-    mu[j] = (center || scale) ? mean : 0.0;  // pca/mod.rs:87-119: mean is stored whenever center||scale
     double is = 1.0;
     if (scale) {
         if (sd > 0.0) is = 1.0 / sd;
         else { is = 0.0; atomicOr(flag, 1u); }  // the reference divides by zero here (NaN columns)
     }
-    inv_sd[j] = is;
+    const double sh = center ? mean : 0.0;  // pca/mod.rs:98-104: subtract only when centring
+    shift[j] = sh, inv_sd[j] = is, shf[j] = (float)sh, isf[j] = (float)is;
+    const double z0 = (0.0 - sh) * is;
+    const __half h = __double2half(z0);
+    zc_h[j] = h;
+    zc_l[j] = __double2half(z0 - (double)__half2float(h));
 }
-// C[i][j] = (G[i][j] - center * n mu_i mu_j) * is_i * is_j    (compact n_sel x n_sel, symmetric)
-__global__ void corr_kernel(const double *__restrict__ G, uint32_t dpad, uint64_t n_sel, const double *__restrict__ mu,
-                            const double *__restrict__ inv_sd, double n_cells, int center, double *__restrict__ C) {
+// compact copy C[i][j] = G[i][j] (n_sel x n_sel out of dpad x dpad). The diagonal is replaced by its exact value
+// sum_cells z^2 = inv_sd^2 (sumsq - 2 shift sum + n shift^2) from the fp64 gene moments (= n when centring and
+// scaling): the diagonal sums only positive terms, which is where fp32 chunk accumulation has a systematic bias.
+__global__ void corr_kernel(const double *__restrict__ G, uint32_t dpad, uint64_t n_sel, const uint32_t *__restrict__ sel,
+                            const double *__restrict__ sum, const double *__restrict__ sq, const double *__restrict__ shift,
+                            const double *__restrict__ inv_sd, double n_cells, double *__restrict__ C) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_sel * n_sel) return;
     const uint64_t i = e / n_sel, j = e % n_sel;
-    double g = G[i * dpad + j];
-    if (center) g -= n_cells * mu[i] * mu[j];
-    C[e] = g * inv_sd[i] * inv_sd[j];
+    double v = G[i * dpad + j];
+    if (i == j) {
+        const uint32_t g = sel[i];
+        const double sh = shift[i], is = inv_sd[i];
+        v = is * is * (sq[g] - 2.0 * sh * sum[g] + n_cells * sh * sh);
+    }
+    C[e] = v;
 }
 __global__ void trace_kernel(const double *__restrict__ C, uint64_t n_sel, double *__restrict__ out) {
     double s = 0.0;
@@ -198,12 +222,10 @@ __global__ void trace_kernel(const double *__restrict__ C, uint64_t n_sel, doubl
 }
 // eigenvectors come back column-major with ascending eigenvalues: column (n_sel-1-c) is component c.
 // Sign convention: the entry of largest magnitude of every component is positive (deterministic across runs).
-// comps[j][c] (row-major n_sel x k), W[p][c] = inv_sd[p] * comps[p][c] (row-major dpad x kpad, zero padded),
-// bias[c] = sum_p mu[p] W[p][c], evr[c] = lambda_c / trace
+// comps[j][c] (row-major n_sel x k), W[p][c] = comps[p][c] (row-major dpad x kpad, zero padded), evr[c] = lambda_c / trace
 __global__ void components_kernel(const double *__restrict__ evec, const double *__restrict__ evals_asc, uint64_t n_sel,
-                                  uint32_t k, uint32_t kpad, const double *__restrict__ mu, const double *__restrict__ inv_sd,
-                                  int center, const double *__restrict__ trace, double *__restrict__ comps,
-                                  double *__restrict__ W, double *__restrict__ bias, double *__restrict__ evr) {
+                                  uint32_t k, uint32_t kpad, const double *__restrict__ trace, double *__restrict__ comps,
+                                  double *__restrict__ W, double *__restrict__ evr) {
     const uint32_t c = blockIdx.x;
     if (c >= k) return;
     const double *v = evec + (n_sel - 1 - c) * n_sel;
@@ -227,51 +249,51 @@ __global__ void components_kernel(const double *__restrict__ evec, const double 
     }
     const double sgn = v[s_idx[0]] < 0.0 ? -1.0 : 1.0;
     __syncthreads();
-    double b = 0.0;
     for (uint64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
         const double x = sgn * v[j];
         comps[j * k + c] = x;
-        const double w = x * inv_sd[j];
-        W[j * kpad + c] = w;
-        b += mu[j] * w;
+        W[j * kpad + c] = x;
     }
-    b = warp_sum(b);
-    if ((threadIdx.x & 31) == 0) s_val[threadIdx.x >> 5] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (unsigned w = 0; w < blockDim.x / 32; ++w) t += s_val[w];
-        bias[c] = center ? t : 0.0;
-        evr[c] = evals_asc[n_sel - 1 - c] / trace[0];
-    }
+    if (threadIdx.x == 0) evr[c] = evals_asc[n_sel - 1 - c] / trace[0];
 }
 
-// K9 (validation path): scores[r][c] = sum_p x[r][p] W[p][c] - bias[c]. One warp per row; the 32 lanes load 32
-// consecutive panel entries, ballot the non-zeros and broadcast each to all lanes; lane l owns components l, l+32.
+// K9 (validation path): scores[r][c] = sum_p z[r][p] W[p][c] in fp64 on CUDA cores. One warp per 4 rows; lane l owns
+// components c0+l and c0+l+32; W rows are read once per 4 rows (L1), z values are warp-broadcast.
 __global__ void __launch_bounds__(256) scores_simt_kernel(const __half *__restrict__ Xh, const __half *__restrict__ Xl,
                                                           uint64_t nrows, uint32_t dpad, const double *__restrict__ W,
-                                                          uint32_t kpad, const double *__restrict__ bias, uint32_t k,
-                                                          uint32_t c0, double *__restrict__ scores) {
+                                                          uint32_t kpad, uint32_t k, uint32_t c0, double *__restrict__ scores) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t)gridDim.x * 8;
-    for (uint64_t r = warp; r < nrows; r += nwarps) {
-        double a0 = 0.0, a1 = 0.0;
-        const __half *xh = Xh + r * dpad, *xl = Xl + r * dpad;
+    for (uint64_t r0 = warp * 4; r0 < nrows; r0 += nwarps * 4) {
+        double acc[4][2] = {};
         for (uint32_t p0 = 0; p0 < dpad; p0 += 32) {
-            const double x = (double)__half2float(xh[p0 + lane]) + (double)__half2float(xl[p0 + lane]);
-            unsigned mask = __ballot_sync(0xffffffffu, x != 0.0);
-            while (mask) {
-                const int src = __ffs(mask) - 1;
-                mask &= mask - 1;
-                const double xv = __shfl_sync(0xffffffffu, x, src);
+            double x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint64_t r = min(r0 + i, nrows - 1);
+                x[i] = (double)__half2float(Xh[r * dpad + p0 + lane]) + (double)__half2float(Xl[r * dpad + p0 + lane]);
+            }
+#pragma unroll 8
+            for (int src = 0; src < 32; ++src) {
                 const double *wr = W + (uint64_t)(p0 + src) * kpad + c0;
-                a0 += xv * wr[lane];
-                a1 += xv * wr[lane + 32];
+                const double w0 = wr[lane], w1 = wr[lane + 32];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double xv = __shfl_sync(0xffffffffu, x[i], src);
+                    acc[i][0] += xv * w0;
+                    acc[i][1] += xv * w1;
+                }
             }
         }
-        if (c0 + lane < k) scores[r * k + c0 + lane] = a0 - bias[c0 + lane];
-        if (c0 + lane + 32 < k) scores[r * k + c0 + lane + 32] = a1 - bias[c0 + lane + 32];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint64_t r = r0 + i;
+            if (r < nrows) {
+                if (c0 + lane < k) scores[r * k + c0 + lane] = acc[i][0];
+                if (c0 + lane + 32 < k) scores[r * k + c0 + lane + 32] = acc[i][1];
+            }
+        }
     }
 }
 
@@ -292,9 +314,11 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     SRB_LAUNCH(lut_set_kernel, nb(n_sel), 256, 0, s, lut->as<int>(), d_sel, n_sel);
 
     Buf flag = dev_zeros(s, 4);
-    Buf mu = dev_alloc(s, 8 * dpad), inv_sd = dev_alloc(s, 8 * dpad);
-    SRB_LAUNCH(sel_stats_kernel, nb(n_sel), 256, 0, s, d_sel, n_sel, m->minor.sum->as<double>(), m->minor.sq->as<double>(),
-               n_cells, center ? 1 : 0, scale ? 1 : 0, mu->as<double>(), inv_sd->as<double>(), flag->as<uint32_t>());
+    Buf shift = dev_alloc(s, 8 * dpad), inv_sd = dev_alloc(s, 8 * dpad), zc_h = dev_alloc(s, 2 * dpad), zc_l = dev_alloc(s, 2 * dpad);
+    Buf shf = dev_alloc(s, 4 * dpad), isf = dev_alloc(s, 4 * dpad);
+    SRB_LAUNCH(sel_stats_kernel, nb(dpad), 256, 0, s, d_sel, n_sel, dpad, m->minor.sum->as<double>(), m->minor.sq->as<double>(),
+               n_cells, center ? 1 : 0, scale ? 1 : 0, shift->as<double>(), inv_sd->as<double>(), shf->as<float>(), isf->as<float>(),
+               zc_h->as<__half>(), zc_l->as<__half>(), flag->as<uint32_t>());
 
     // K6 panels
     Buf Xh = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad), Xl = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad);
@@ -304,10 +328,10 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
         const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 16);
         if (m->vdtype == SRB_F32) {
             SRB_CUDA(cudaFuncSetAttribute(densify_panels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut->as<int>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+            SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut->as<int>(), shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
             SRB_CUDA(cudaFuncSetAttribute(densify_panels_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+            SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         }
     }
     // K7 Gram
@@ -332,24 +356,24 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     }
     // K8: correlation matrix + symmetric eigendecomposition
     Buf C = dev_alloc(s, 8 * n_sel * n_sel), evals = dev_alloc(s, 8 * n_sel), tr = dev_alloc(s, 8);
-    Buf comps = dev_alloc(s, 8 * n_sel * k), W = dev_zeros(s, 8 * (size_t)dpad * kpad), bias = dev_zeros(s, 8 * kpad), evr = dev_alloc(s, 8 * k);
+    Buf comps = dev_alloc(s, 8 * n_sel * k), W = dev_zeros(s, 8 * (size_t)dpad * kpad), evr = dev_alloc(s, 8 * k);
     {
         StageTimer t(c, ST_EIG);
-        SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, G->as<double>(), dpad, n_sel, mu->as<double>(), inv_sd->as<double>(), n_cells, center ? 1 : 0, C->as<double>());
+        SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, G->as<double>(), dpad, n_sel, d_sel, m->minor.sum->as<double>(), m->minor.sq->as<double>(), shift->as<double>(), inv_sd->as<double>(), n_cells, C->as<double>());
         SRB_LAUNCH(trace_kernel, 1, 256, 0, s, C->as<double>(), n_sel, tr->as<double>());
         sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, evals->as<double>());
-        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), n_sel, (uint32_t)k, kpad, mu->as<double>(), inv_sd->as<double>(), center ? 1 : 0, tr->as<double>(), comps->as<double>(), W->as<double>(), bias->as<double>(), evr->as<double>());
+        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), n_sel, (uint32_t)k, kpad, tr->as<double>(), comps->as<double>(), W->as<double>(), evr->as<double>());
     }
     // K9 scores
     Buf scores = dev_alloc(s, 8 * std::max<uint64_t>(n, 1) * k);
     if (n) {
         StageTimer t(c, ST_SCORES);
-        if (gram_mode == 0) {
-            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), bias->as<double>(), (uint32_t)k, scores->as<double>());
+        if (gram_mode == 0 && k <= 64) {
+            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, (uint32_t)k, scores->as<double>());
         } else {
-            const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 32);
+            const unsigned grid = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)c->sm_count * 16);
             for (uint32_t c0 = 0; c0 < k; c0 += 64)
-                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, bias->as<double>(), (uint32_t)k, c0, scores->as<double>());
+                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, (uint32_t)k, c0, scores->as<double>());
         }
     }
     if (out.scores && n) SRB_CUDA(cudaMemcpyAsync(out.scores, scores->p, 8 * n * k, cudaMemcpyDeviceToHost, s));

@@ -35,7 +35,7 @@ __global__ void stream_var_kernel(const double *cnt, const double *sum, const do
     double r = 0.0;
     if (cnt[j] > 0.0) {
         const double mean = sum[j] / cnt[j];
-        r = sq[j] / cnt[j] - mean * mean;
+        r = __dsub_rn(__ddiv_rn(sq[j], cnt[j]), __dmul_rn(mean, mean));
     }
     out[j] = r;
 }

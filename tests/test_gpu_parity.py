@@ -364,3 +364,35 @@ def test_pipeline_call_equals_separate_calls(ffi, ctx):
     np.testing.assert_allclose(r1["scores"], r2["scores"], rtol=1e-9, atol=1e-9)
     st = ctx.last_stage_ms()
     assert st["gram"] > 0 and st["eig"] > 0
+
+
+@pytest.mark.parametrize("n,m,n_top,k", [(3000, 400, 100, 10), (20000, 900, 600, 20), (1000, 300, 257, 5)])
+def test_pca_tensor_core_gram_matches_fp64_and_oracle(ffi, ctx, n, m, n_top, k):
+    """tcgen05 Gram (split-fp16 operands, fp32 TMEM chunks, fp64 across chunks) vs the fp64 CUDA-core path and the
+    oracle's exact SVD. Tolerance: north_star 1e-5 relative on loadings / explained variance."""
+    rng = np.random.default_rng(77 + n)
+    a = clustered_counts(rng, n, m)
+    mt, mf = upload(ffi, ctx, a), upload(ffi, ctx, a)
+    for mm in (mt, mf):
+        mm.normalize_total_inplace(1e4, ffi.ROW)
+        mm.log1p_inplace()
+    sel = mt.select_hvg(n_top)
+    rt = mt.pca(sel, k, gram_mode=ffi.GRAM_TENSOR)
+    rf = mf.pca(sel, k, gram_mode=ffi.GRAM_FP64)
+    print("evr rel diff tensor vs fp64:", np.max(np.abs(rt["explained_variance_ratio"] / rf["explained_variance_ratio"] - 1)))
+    # oracle on the device's (f32-stored) values so the comparison isolates the PCA stage
+    off, idx, val = mt.download()
+    ol = O.Compressed("csr", n, m, off, idx, val)
+    want = P.pca_pipeline(ol, n_top, k, selection=sel)
+    good = well_separated(want["eigenvalues"], k)
+    comps = sign_align(rt["components"], want["components"])
+    scores = sign_align(rt["scores"], want["scores"])
+    cerr = [float(np.max(np.abs(comps[:, j] - want["components"][:, j]))) for j in range(k)]
+    serr = [float(np.max(np.abs(scores[:, j] - want["scores"][:, j])) / (np.linalg.norm(want["scores"][:, j]) / np.sqrt(n))) for j in range(k)]
+    print("component max-abs errors:", ["%.1e" % e for e in cerr], "score errors / rms:", ["%.1e" % e for e in serr], "good:", good)
+    np.testing.assert_allclose(rt["explained_variance_ratio"], rf["explained_variance_ratio"], rtol=RTOL)
+    np.testing.assert_allclose(rt["explained_variance_ratio"], want["explained_variance_ratio"], rtol=RTOL)
+    for j in np.nonzero(good)[0]:
+        assert cerr[j] <= RTOL, (j, cerr)
+        assert serr[j] <= 10 * RTOL, (j, serr)
+    assert good[:3].all()
