@@ -1,0 +1,2 @@
+"""Mirror of the reference's src/backed front-end (out-of-core data)."""
+from . import statistics  # noqa: F401

@@ -398,24 +398,33 @@ static void ensure_range_all(srb_mat *m) {
 //  * quantisation keeps every value to <= 2^-17 relative: either integer-valued data below 2^28 (exact), or a
 //    dynamic range max/min <= 4096 of the values whose moments are taken
 //  * FAITHFUL f64 storage asks for the reference's f64 accumulation instead
-static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, int out_dtype) {
+// dec[0] = hi, dec[1] = -lo, dec[2..4] = flags (as doubles) so that one MAX-allreduce makes the decision (and the
+// fixed-point scale F derived from dec[0]) identical on every rank of a row-sharded job
+__global__ void decision_pack_kernel(const double *__restrict__ range, const uint32_t *__restrict__ flags, double *__restrict__ dec) {
+    dec[0] = range[0];
+    dec[1] = -range[1];
+    dec[2] = (double)flags[0], dec[3] = (double)flags[1], dec[4] = (double)flags[2];
+}
+static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, int out_dtype, Buf &dec_out) {
     int S;
     uint32_t W;
     stripe_plan(m, &S, &W);
     if (S > kMaxStripes) return false;
     if (m->ctx->value_mode == SRB_VALUES_FAITHFUL && out_dtype == SRB_F64) return false;
-    uint32_t flags[3];
-    double rng[2];
     cudaStream_t s = m->ctx->stream;
-    SRB_CUDA(cudaMemcpyAsync(flags, m->major.flags->as<uint32_t>(), sizeof(flags), cudaMemcpyDeviceToHost, s));
-    SRB_CUDA(cudaMemcpyAsync(rng, range->p, sizeof(rng), cudaMemcpyDeviceToHost, s));
+    Buf dec = dev_alloc(s, 5 * sizeof(double));
+    SRB_LAUNCH(decision_pack_kernel, 1, 1, 0, s, range->as<double>(), m->major.flags->as<uint32_t>(), dec->as<double>());
+    if (m->ctx->nranks > 1 && m->format == SRB_CSR) allreduce_f64_max(m->ctx, dec->as<double>(), 5);
+    double h[5];
+    SRB_CUDA(cudaMemcpyAsync(h, dec->p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SRB_CUDA(cudaStreamSynchronize(s));
-    if (flags[0] || flags[1]) return false;
-    double hi = rng[0], lo = rng[1];
+    dec_out = dec;  // dec[0] is the (global) upper bound the fixed-point scale is derived from
+    if (h[2] != 0.0 || h[3] != 0.0) return false;
+    double hi = h[0], lo = -h[1];
     if (!(hi >= 0.0) || !std::isfinite(hi)) return false;
     if (lg) hi = std::log1p(hi), lo = std::log1p(lo);
-    if (!pending && !flags[2] && hi < 268435456.0) return true;  // integers: exactly representable
-    if (hi == 0.0 || std::isinf(lo)) return true;                // all zeros
+    if (!pending && h[4] == 0.0 && hi < 268435456.0) return true;  // integers: exactly representable
+    if (hi == 0.0 || std::isinf(lo)) return true;                  // all zeros
     return lo > 0.0 && hi / lo <= 4096.0;
 }
 
@@ -454,7 +463,9 @@ void materialize(srb_mat *m, bool want_moments) {
             ensure_range_all(m);
             bound = m->absmax_all;
         }
-        exact = m->major.valid && exact_path_ok(m, bound, pending, pending && m->pend_log1p, out_dtype);
+        Buf dec;
+        exact = m->major.valid && exact_path_ok(m, bound, pending, pending && m->pend_log1p, out_dtype, dec);
+        if (exact) bound = dec;
     }
 
     Buf new_values = m->values;
