@@ -2,6 +2,10 @@
 // direction dispatch that mirrors src/shared/statistics/mod.rs (ArrayData::{CsrMatrix,CscMatrix} -> helper).
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -12,17 +16,72 @@ static thread_local std::string t_last_error;
 std::atomic<uint64_t> g_launches{0};
 void set_last_error(const std::string &msg) { t_last_error = msg; }
 
+// ---- device memory: per-stream block cache ----------------------------------------------------------------------
+// Every buffer of a context lives on that context's single stream, so a block released by ~DevBuf can be handed to
+// the next request in program order without any event bookkeeping. Steady-state steps therefore never reach the
+// driver allocator (measured: cudaMallocAsync pool growth stalls of 40-700 ms per step otherwise). Best fit within
+// 25 %; blocks beyond a 64 GB cache budget are returned to the driver.
+struct BlockCache {
+    std::multimap<size_t, void *> free_blocks;
+    size_t cached_bytes = 0;
+};
+static std::mutex g_cache_mu;
+static std::map<cudaStream_t, BlockCache> g_caches;
+static constexpr size_t kCacheBudget = 64ull << 30;
+
+static size_t round_block(size_t n) {
+    if (n < 512) return 512;
+    if (n < (1u << 20)) return (n + 511) & ~size_t(511);
+    return (n + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+}
+
 DevBuf::DevBuf(size_t n, cudaStream_t s) : bytes(n), st(s) {
-    if (n == 0) n = 16;
-    cudaError_t e = cudaMallocAsync(&p, n, s);
+    cap = round_block(n);
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        BlockCache &c = g_caches[s];
+        auto it = c.free_blocks.lower_bound(cap);
+        if (it != c.free_blocks.end() && it->first <= cap + cap / 4 + (size_t(1) << 20)) {
+            p = it->second;
+            cap = it->first;
+            c.cached_bytes -= cap;
+            c.free_blocks.erase(it);
+            return;
+        }
+    }
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        release_cached_blocks(s);  // give everything back and retry once
+        e = cudaMalloc(&p, cap);
+    }
     if (e != cudaSuccess) {
         p = nullptr;
         cudaGetLastError();
-        throw Error(SRB_ERR_OOM, std::string("cudaMallocAsync(") + std::to_string(n) + "): " + cudaGetErrorString(e));
+        throw Error(SRB_ERR_OOM, std::string("cudaMalloc(") + std::to_string(cap) + "): " + cudaGetErrorString(e));
     }
 }
 DevBuf::~DevBuf() {
-    if (p) cudaFreeAsync(p, st);
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    BlockCache &c = g_caches[st];
+    c.free_blocks.emplace(cap, p);
+    c.cached_bytes += cap;
+    while (c.cached_bytes > kCacheBudget && !c.free_blocks.empty()) {
+        auto it = std::prev(c.free_blocks.end());
+        cudaFree(it->second);
+        c.cached_bytes -= it->first;
+        c.free_blocks.erase(it);
+    }
+}
+void release_cached_blocks(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto f = g_caches.find(s);
+    if (f == g_caches.end()) return;
+    cudaStreamSynchronize(s);
+    for (auto &kv : f->second.free_blocks) cudaFree(kv.second);
+    f->second.free_blocks.clear();
+    f->second.cached_bytes = 0;
 }
 Buf dev_alloc(cudaStream_t st, size_t bytes) { return std::make_shared<DevBuf>(bytes, st); }
 Buf dev_zeros(cudaStream_t st, size_t bytes) {
@@ -31,13 +90,39 @@ Buf dev_zeros(cudaStream_t st, size_t bytes) {
     return b;
 }
 
+static bool debug_timing() {
+    static int v = -1;
+    if (v < 0) v = getenv("SRB_DEBUG_TIMING") ? 1 : 0;
+    return v == 1;
+}
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+void trace_point(const char *label) {
+    if (!debug_timing()) return;
+    static double last = 0.0;
+    const double t = now_ms();
+    fprintf(stderr, "[srb]   %-28s +%.2f ms\n", label, last == 0.0 ? 0.0 : t - last);
+    last = t;
+}
 StageTimer::StageTimer(srb_ctx *ctx, int stage) : c(ctx), s(stage) {
     if (!c->ev_used[s]) {
         cudaEventRecord(c->ev0[s], c->stream);
         c->ev_used[s] = true;
     }
+    if (debug_timing()) {
+        cudaStreamSynchronize(c->stream);
+        t0 = now_ms();
+    }
 }
-StageTimer::~StageTimer() { cudaEventRecord(c->ev1[s], c->stream); }
+StageTimer::~StageTimer() {
+    cudaEventRecord(c->ev1[s], c->stream);
+    if (debug_timing()) {
+        const double t1 = now_ms();
+        cudaStreamSynchronize(c->stream);
+        fprintf(stderr, "[srb] stage %d: host enqueue %.2f ms, until done %.2f ms\n", s, t1 - t0, now_ms() - t0);
+    }
+}
 
 // ---- conversion kernels ------------------------------------------------------------------------------
 template <typename SRC, typename DST>
@@ -220,11 +305,6 @@ int32_t srb_ctx_create(int32_t device, srb_ctx **out) {
         SRB_CUDA(cudaEventCreate(&c->ev0[i]));
         SRB_CUDA(cudaEventCreate(&c->ev1[i]));
     }
-    // keep freed blocks in the stream-ordered pool: steady-state steps never hit cudaMalloc
-    cudaMemPool_t pool;
-    SRB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    SRB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     *out = c.release();
     SRB_API_END
 }
@@ -234,6 +314,7 @@ int32_t srb_ctx_destroy(srb_ctx *ctx) {
     if (!ctx) return SRB_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    release_cached_blocks(ctx->stream);
     comm_destroy(ctx);
     eig_destroy(ctx);
     for (int i = 0; i < ST_COUNT; ++i) {
@@ -613,13 +694,17 @@ int32_t srb_pipeline_normalize_hvg_pca(srb_mat *m, double target_sum, uint64_t n
     srb_ctx *c = m->ctx;
     SRB_CUDA(cudaSetDevice(c->device));
     reset_stage_timers(c);
+    SRB_TRACE("pipeline begin");
     set_pending_normalize(m, target_sum, SRB_ROW);
+    SRB_TRACE("set_pending_normalize");
     set_pending_log1p(m);
+    SRB_TRACE("set_pending_log1p");
     Buf d_idx;
     uint64_t n_sel = 0;
     {
         select_hvg_device(m, n_top, d_idx, &n_sel, true);
     }
+    SRB_TRACE("select_hvg_device");
     if (hvg_out) {
         std::vector<uint32_t> h(n_sel);
         d2h(c, h.data(), d_idx->p, 4 * n_sel);

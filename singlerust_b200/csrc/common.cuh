@@ -63,10 +63,11 @@ extern std::atomic<uint64_t> g_launches;
         return SRB_ERR_INVALID_ARG;                                                                          \
     }
 
-// stream-ordered device buffer; freed on the owning stream when the last reference drops
+// device buffer owned by one context stream; returned to that stream's block cache when the last reference drops
+void release_cached_blocks(cudaStream_t s);
 struct DevBuf {
     void *p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0, cap = 0;
     cudaStream_t st = nullptr;
     DevBuf(size_t n, cudaStream_t s);
     ~DevBuf();
@@ -164,9 +165,14 @@ struct srb_mat {
 
 namespace srb {
 
+// debug tracing of host-side time (SRB_DEBUG_TIMING=1)
+void trace_point(const char *label);
+#define SRB_TRACE(label) srb::trace_point(label)
+
 struct StageTimer {
     srb_ctx *c;
     int s;
+    double t0 = 0.0;
     StageTimer(srb_ctx *ctx, int stage);
     ~StageTimer();
 };

@@ -62,9 +62,11 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
         SRB_LAUNCH((densify_f64_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), row0, nrows, n_sel, d_out);
 }
 
-// K6: CSR rows -> standardised split-fp16 panels. One warp per row builds the dpad-wide row in shared memory: every
-// column starts at the constant z of an implicit zero, (0 - shift_j) * inv_sd_j, then the stored entries are
-// scattered over it; the row is written out with 16-byte coalesced stores. HBM: 8 B/nnz in, 4*dpad B/row out.
+// K6: CSR rows -> standardised split-fp16 panels, one warp per row, no shared memory (64 resident warps per SM hide the
+// HBM latency). Step 1 streams the row of implicit-zero constants (0 - shift_j) * inv_sd_j to global memory with
+// 16-byte stores; step 2 overwrites the stored entries with 2-byte scattered stores — they hit the lines step 1 just
+// put into L2, so DRAM sees each line once. __syncwarp() orders the two steps inside the warp.
+// HBM: 8 B/nnz in, 4*dpad B/row out.
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const int *__restrict__ lut,
@@ -72,32 +74,43 @@ __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__re
                                                              const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
                                                              uint64_t nrows, uint32_t dpad, __half *__restrict__ Xh,
                                                              __half *__restrict__ Xl) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __half *rh = reinterpret_cast<__half *>(smem_raw) + (size_t)w * 2 * dpad;
-    __half *rl = rh + dpad;
-    const uint64_t warp = (uint64_t)blockIdx.x * 8 + w;
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t)gridDim.x * 8;
     const uint32_t nvec = dpad / 8;  // uint4 = 8 halves
     const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
+    constexpr int kBatch = 8;
     for (uint64_t r = warp; r < nrows; r += nwarps) {
-        uint4 *zh = reinterpret_cast<uint4 *>(rh), *zl = reinterpret_cast<uint4 *>(rl);
-        for (uint32_t i = lane; i < nvec; i += 32) zh[i] = ch[i], zl[i] = cl[i];
-        __syncwarp();
         const int64_t a = off[r], b = off[r + 1];
-        for (int64_t k = a + lane; k < b; k += 32) {
-            const int p = lut[idx[k]];
-            if (p >= 0) {
-                // fp32 is enough here: the split keeps 22 bits of z, fp32 carries 24
-                const float z = ((float)val[k] - shf[p]) * isf[p];
-                const __half h = __float2half_rn(z);
-                rh[p] = h;
-                rl[p] = __float2half_rn(z - __half2float(h));
+        uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
+        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
+        __syncwarp();
+        __half *rh = Xh + r * dpad, *rl = Xl + r * dpad;
+        for (int64_t k0 = a + lane; k0 < b; k0 += 32 * kBatch) {
+            uint32_t cc[kBatch];
+            float vv[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int64_t k = k0 + 32 * u;
+                const bool in = k < b;
+                cc[u] = in ? idx[k] : 0xFFFFFFFFu;
+                vv[u] = in ? (float)val[k] : 0.f;
+            }
+            int pp[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) pp[u] = cc[u] != 0xFFFFFFFFu ? lut[cc[u]] : -1;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int p = pp[u];
+                if (p >= 0) {
+                    // fp32 is enough here: the split keeps 22 bits of z, fp32 carries 24
+                    const float z = (vv[u] - shf[p]) * isf[p];
+                    const __half h = __float2half_rn(z);
+                    rh[p] = h;
+                    rl[p] = __float2half_rn(z - __half2float(h));
+                }
             }
         }
-        __syncwarp();
-        uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
-        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = zh[i], ol[i] = zl[i];
         __syncwarp();
     }
 }
@@ -305,7 +318,9 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     const uint64_t n = m->nrows, M = m->nminor();
     const double n_cells = (double)(c->nranks > 1 ? m->global_nrows : m->nrows);
     SRB_REQUIRE(n_cells >= 2, SRB_ERR_INVALID_ARG, "PCA needs at least two cells");
+    SRB_TRACE("pca_run begin");
     ensure_minor_moments(m);  // also applies pending transforms (fused)
+    SRB_TRACE("ensure_minor_moments");
 
     const uint32_t dpad = (uint32_t)((n_sel + 255) / 256 * 256);
     const uint32_t kpad = (uint32_t)((k + 63) / 64 * 64);
@@ -320,20 +335,20 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
                n_cells, center ? 1 : 0, scale ? 1 : 0, shift->as<double>(), inv_sd->as<double>(), shf->as<float>(), isf->as<float>(),
                zc_h->as<__half>(), zc_l->as<__half>(), flag->as<uint32_t>());
 
+    SRB_TRACE("lut + sel_stats");
     // K6 panels
     Buf Xh = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad), Xl = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad);
     if (n) {
         StageTimer t(c, ST_DENSIFY);
-        const size_t smem = (size_t)8 * 2 * dpad * sizeof(__half);
-        const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 16);
+        const size_t smem = 0;
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8 * 4);
         if (m->vdtype == SRB_F32) {
-            SRB_CUDA(cudaFuncSetAttribute(densify_panels_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut->as<int>(), shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
-            SRB_CUDA(cudaFuncSetAttribute(densify_panels_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         }
     }
+    SRB_TRACE("panels alloc + densify enqueue");
     // K7 Gram
     Buf G = dev_zeros(s, 8 * (size_t)dpad * dpad);
     {
@@ -350,6 +365,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             SRB_LAUNCH(gram_mirror_kernel, nb((uint64_t)dpad * dpad), 256, 0, s, G->as<double>(), dpad, (uint32_t)GT);
         }
     }
+    SRB_TRACE("gram");
     if (c->nranks > 1) {
         StageTimer t(c, ST_ALLREDUCE);
         allreduce_f64_sum(c, G->as<double>(), (size_t)dpad * dpad);
@@ -364,6 +380,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
         sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, evals->as<double>());
         SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), n_sel, (uint32_t)k, kpad, tr->as<double>(), comps->as<double>(), W->as<double>(), evr->as<double>());
     }
+    SRB_TRACE("eig");
     // K9 scores
     Buf scores = dev_alloc(s, 8 * std::max<uint64_t>(n, 1) * k);
     if (n) {
@@ -379,9 +396,11 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     if (out.scores && n) SRB_CUDA(cudaMemcpyAsync(out.scores, scores->p, 8 * n * k, cudaMemcpyDeviceToHost, s));
     if (out.components) SRB_CUDA(cudaMemcpyAsync(out.components, comps->p, 8 * n_sel * k, cudaMemcpyDeviceToHost, s));
     if (out.evr) SRB_CUDA(cudaMemcpyAsync(out.evr, evr->p, 8 * k, cudaMemcpyDeviceToHost, s));
+    SRB_TRACE("scores enqueue");
     uint32_t hflag = 0;
     SRB_CUDA(cudaMemcpyAsync(&hflag, flag->p, 4, cudaMemcpyDeviceToHost, s));
     SRB_CUDA(cudaStreamSynchronize(s));
+    SRB_TRACE("final sync");
     SRB_REQUIRE(!hflag, SRB_ERR_NAN, "a selected feature has zero variance over all cells while scale=true (the reference divides by zero: NaN scores)");
 }
 
