@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--hvg", type=int, default=2000)
     ap.add_argument("--pcs", type=int, default=50)
     ap.add_argument("--gram-mode", type=int, default=int(os.environ.get("SRB_GRAM_MODE", "0")), help="0 tcgen05, 1 fp64 CUDA cores")
+    ap.add_argument("--inflight", type=int, default=1, help="batches in flight per GPU (one context + stream + host thread each): "
+                    "the latency-bound eigensolver of batch i overlaps the bandwidth-bound kernels of batch i+1")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -174,7 +176,7 @@ def run_reference(args):
 def workload_config(args, sample_cells=None):
     return {"workload": "configs[2]: 1M cells x 30k genes CSR 5% nnz per GPU: normalise + log1p + HVG(top 2k) + 50-PC PCA",
             "cells_per_gpu": args.cells if sample_cells is None else sample_cells, "genes": args.genes, "hvg": args.hvg,
-            "pcs": args.pcs, "target_sum": TARGET_SUM, "seed": f"0x{SEED:X}", "parallelism": f"row-shard x{args.gpus}",
+            "pcs": args.pcs, "target_sum": TARGET_SUM, "seed": f"0x{SEED:X}", "parallelism": f"row-shard x{args.gpus}", "batches_in_flight_per_gpu": getattr(args, "inflight", 1),
             "l2": "inputs (12 GB/GPU) are larger than L2; no explicit flush"}
 
 
@@ -196,46 +198,65 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    ctx = _ffi.Context(local_rank)
+    L = max(1, args.inflight)
+    ctxs = [_ffi.Context(local_rank) for _ in range(L)]
     if world > 1:
-        obj = [_ffi.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(obj, src=0)
-        ctx.comm_init(obj[0], rank, world)
+        for c in ctxs:  # one NCCL communicator per in-flight lane
+            obj = [_ffi.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(obj, src=0)
+            c.comm_init(obj[0], rank, world)
+    ctx = ctxs[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        ctx.synchronize()
+        for c in ctxs:
+            c.synchronize()
 
     thr, amp = synth.gene_tables(args.genes, seed=SEED, mean_density=0.05)
-    mat = _ffi.DeviceMatrix.synth(ctx, SEED, args.cells, args.genes, thr, amp, row0=rank * args.cells)
-    mat.set_shard(rank * args.cells, world * args.cells)
+    mats = []
+    for c in ctxs:  # every lane owns a device-resident copy of the rank's shard (same seed => identical data)
+        mt = _ffi.DeviceMatrix.synth(c, SEED, args.cells, args.genes, thr, amp, row0=rank * args.cells)
+        mt.set_shard(rank * args.cells, world * args.cells)
+        mats.append(mt)
+    mat = mats[0]
     info = mat.info()
     nnz = info["nnz"]
 
-    def step():
-        t0 = time.perf_counter()
-        work = mat.clone()  # copy-on-write: the fused kernel reads the raw counts and writes a fresh value buffer
-        t1 = time.perf_counter()
+    def step(lane=0):
+        work = mats[lane].clone()  # copy-on-write: the fused kernel reads the raw counts and writes a fresh value buffer
         work.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, want_outputs=False)
-        t2 = time.perf_counter()
-        st = ctx.last_stage_ms()
-        t3 = time.perf_counter()
+        st = ctxs[lane].last_stage_ms()
         work.free()
-        if args.verbose and rank == 0:
-            print(f"  clone {1e3*(t1-t0):.1f} pipeline {1e3*(t2-t1):.1f} stage_query {1e3*(t3-t2):.1f} free {1e3*(time.perf_counter()-t3):.1f}", file=sys.stderr)
         return st
 
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    for _ in range(args.warmup):
-        step()
-    # untimed settling: lazily-loaded library modules (cuSOLVER) and the memory pool reach steady state at different
-    # speeds on a cold box; keep stepping (at most 8 more) until two consecutive steps agree within 5 %
+    def run_steps(n_steps):
+        """n_steps pipeline passes, round-robin over the lanes, one host thread per lane. Returns the stage times."""
+        out = [[] for _ in range(L)]
+
+        def worker(lane):
+            for _ in range(lane, n_steps, L):
+                out[lane].append(step(lane))
+
+        if L == 1:
+            worker(0)
+        else:
+            ts = [threading.Thread(target=worker, args=(lane,)) for lane in range(L)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return [s for lane in out for s in lane]
+
+    streams = [torch.cuda.ExternalStream(c.stream, device=dev) for c in ctxs]
+    run_steps(max(args.warmup, L))
+    # untimed settling: lazily-loaded library modules (cuSOLVER) reach steady state at different speeds on a cold
+    # box; keep stepping (at most 8 more rounds) until two consecutive rounds agree within 5 %
     prev = None
     for _ in range(8):
         t0 = time.perf_counter()
-        step()
+        run_steps(L)
         dt = time.perf_counter() - t0
         if prev is not None and abs(dt - prev) <= 0.05 * prev:
             break
@@ -245,20 +266,19 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.25)
     launches0 = _ffi.kernel_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
     barrier()
     t_wall0 = time.time()
-    e0.record(stream)
-    stages = []
-    for _ in range(args.steps):
-        tw = time.perf_counter()
-        stages.append(step())
-        if args.verbose and rank == 0:
-            print(f"step wall {1e3 * (time.perf_counter() - tw):.2f} ms", stages[-1], file=sys.stderr)
-    e1.record(stream)
+    for e, st_ in zip(ev0, streams):
+        e.record(st_)
+    stages = run_steps(args.steps)
+    for e, st_ in zip(ev1, streams):
+        e.record(st_)
     barrier()
     t_wall1 = time.time()
-    ms_total = e0.elapsed_time(e1)
+    # device time of the region: earliest start event to latest end event (all lanes are on the same device)
+    ms_total = max(a.elapsed_time(b) for a in ev0 for b in ev1)
     launches = _ffi.kernel_launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -318,8 +338,10 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "error": str(ex)[:300]}
     if rank == 0:
         print(json.dumps(line))
-    mat.free()
-    ctx.close()
+    for mt in mats:
+        mt.free()
+    for c in ctxs:
+        c.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -175,7 +175,7 @@ int32_t srb_pipeline_normalize_hvg_pca(srb_mat *m, double target_sum, uint64_t n
 
 /* per-stage device times (ms) of the last srb_pca / srb_pipeline_* call on this matrix's ctx, measured with
  * CUDA events on the ctx stream: [0] row sums, [1] fused normalise+log1p+gene moments, [2] hvg select,
- * [3] densify, [4] gram, [5] eig, [6] scores, [7] allreduce. n = capacity of out_ms. */
+ * [3] densify, [4] gram, [5] eig, [6] scores, [7] moments allreduce, [8] gram allreduce. n = capacity of out_ms. */
 int32_t srb_last_stage_ms(srb_ctx *ctx, float *out_ms, int32_t n);
 
 #ifdef __cplusplus

@@ -20,7 +20,8 @@ DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np
           np.dtype(np.float32): 8, np.dtype(np.float64): 9}
 F32, F64 = 8, 9
 
-STAGES = ["row_sums", "fused_norm_log1p_moments", "hvg_select", "densify", "gram", "eig", "scores", "allreduce"]
+STAGES = ["row_sums", "fused_norm_log1p_moments", "hvg_select", "densify", "gram", "eig", "scores", "allreduce_moments",
+          "allreduce_gram"]
 
 
 class SrbError(RuntimeError):

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -26,6 +27,8 @@ struct NcclApi {
 
 static NcclApi &nccl() {
     static NcclApi api;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     if (!api.lib) {
         api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);

@@ -82,7 +82,7 @@ using Buf = std::shared_ptr<DevBuf>;
 Buf dev_alloc(cudaStream_t st, size_t bytes);
 Buf dev_zeros(cudaStream_t st, size_t bytes);
 
-enum Stage { ST_ROWSUM = 0, ST_FUSED = 1, ST_HVG = 2, ST_DENSIFY = 3, ST_GRAM = 4, ST_EIG = 5, ST_SCORES = 6, ST_ALLREDUCE = 7, ST_COUNT = 8 };
+enum Stage { ST_ROWSUM = 0, ST_FUSED = 1, ST_HVG = 2, ST_DENSIFY = 3, ST_GRAM = 4, ST_EIG = 5, ST_SCORES = 6, ST_ALLREDUCE = 7, ST_ALLREDUCE_GRAM = 8, ST_COUNT = 9 };
 
 struct NcclApi;  // dlopen'ed table (comm.cu)
 

@@ -51,23 +51,26 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
             if (MODE == MODE_SUM_ABSMAX && sizeof(VT) == 4) {
                 // f32 fast path: range / sign / finiteness / integrality tracked on the raw bit patterns (integer
                 // min/max and one OR per element) so that the loop stays bandwidth- rather than issue-bound;
-                // 8 independent loads in flight per lane.
+                // 16 independent loads in flight per lane.
                 uint32_t orbits = 0, maxab = 0, minab1 = 0xFFFFFFFFu, nonint = 0;
                 const float *fv = reinterpret_cast<const float *>(val);
-                for (; k < b; k += 8 * LPR) {
-                    float v[8];
+                constexpr int U = 16;
+                for (; k < b; k += U * LPR) {
+                    float v[U];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = (k + u * LPR < b) ? fv[k + u * LPR] : 0.f;
+                    for (int u = 0; u < U; ++u) v[u] = (k + u * LPR < b) ? fv[k + u * LPR] : 0.f;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         const uint32_t bits = __float_as_uint(v[u]), ab = bits & 0x7FFFFFFFu;
                         orbits |= bits;
                         maxab = max(maxab, ab);
                         minab1 = min(minab1, ab - 1u);  // zeros wrap to 0xFFFFFFFF and drop out of the minimum
                         nonint |= (uint32_t)(v[u] != truncf(v[u]));
                     }
-                    s0 += (double)v[0] + (double)v[4], s1 += (double)v[1] + (double)v[5];
-                    s2 += (double)v[2] + (double)v[6], s3 += (double)v[3] + (double)v[7];
+#pragma unroll
+                    for (int u = 0; u < U; u += 4) {
+                        s0 += (double)v[u], s1 += (double)v[u + 1], s2 += (double)v[u + 2], s3 += (double)v[u + 3];
+                    }
                 }
                 mx = (double)__uint_as_float(maxab);
                 mnz = (minab1 == 0xFFFFFFFFu) ? INFINITY : (double)__uint_as_float(minab1 + 1u);

@@ -138,7 +138,6 @@ struct FusedParams {
     uint32_t rows_per_block;
     const int *fexp;
     unsigned long long *acc;  // 6 * nminor: cnt, sumA, sumB, sqA, sqB, sqC
-    unsigned long long *range_bits;  // [0] max, [1] min positive of the produced values
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -166,7 +165,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
 
     const bool has_scale = p.scale != nullptr;
     const bool lg = p.do_log1p != 0;
-    VTO local_max = 0, local_min = INFINITY;
 
     // Memory-level parallelism: the row's segment bounds are fetched one row ahead and the nnz are read in batches of
     // kBatch independent 128-byte warp loads per array before any of them is consumed (the ncu source view of the first
@@ -182,39 +180,44 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
         const uint64_t rn = r + kFusedThreads / 32;
         if (rn < r1) a_next = seg_lo(rn), b_next = seg_hi(rn);
         const double sc_row = (has_scale && p.scale_major) ? p.scale[r] : 1.0;
-        for (int64_t k0 = a + lane; k0 < b; k0 += 32 * kBatch) {
+        // 32-bit offsets relative to the segment start keep the address arithmetic to one IMAD.WIDE per access
+        const uint32_t *ip = p.idx + a;
+        const VTI *vp = vin + a;
+        VTO *op = vout + a;
+        const int len = (int)(b - a);
+        for (int k0 = lane; k0 < len; k0 += 32 * kBatch) {
             uint32_t cc[kBatch];
             VTI vv[kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int64_t k = k0 + 32 * u;
-                const bool in = k < b;
-                cc[u] = in ? p.idx[k] : 0u;
-                vv[u] = in ? vin[k] : (VTI)0;
+                const int k = k0 + 32 * u;
+                const bool in = k < len;
+                cc[u] = in ? ip[k] : 0u;
+                vv[u] = in ? vp[k] : (VTI)0;
             }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int64_t k = k0 + 32 * u;
-                if (k < b) {
+                const int k = k0 + 32 * u;
+                if (k < len) {
                     const uint32_t c = cc[u];
                     const double sc = (has_scale && !p.scale_major) ? p.scale[c] : sc_row;
                     const VTO x = Xform<VTO>::apply(vv[u], sc, has_scale, lg);
-                    if (WRITE) vout[k] = x;
-                    local_max = x > local_max ? x : local_max;
-                    local_min = (x > 0 && x < local_min) ? x : local_min;
+                    if (WRITE) op[k] = x;
                     uint32_t q;
                     if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
                     else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
                     const uint32_t g = c - col_lo;
                     const uint32_t o1 = atomicAdd(&s_sum[g], q);
-                    const uint32_t c1 = (uint32_t)((o1 + q) < o1);
                     const unsigned long long q2 = (unsigned long long)q * q;
                     const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
                     const uint32_t o2 = atomicAdd(&s_sqlo[g], l);
-                    const uint32_t add3 = h + (uint32_t)((o2 + l) < o2);
+                    uint32_t c1, add3, c3, t0;
+                    // carries through add.cc / addc instead of compare + select
+                    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c1) : "r"(o1), "r"(q));
+                    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t0), "=r"(add3) : "r"(o2), "r"(l), "r"(h));
                     const uint32_t o3 = atomicAdd(&s_sqmid[g], add3);
-                    const uint32_t c3 = (uint32_t)((o3 + add3) < o3);
-                    atomicAdd(&s_pack[g], (1u << 18) | (c1 << 6) | c3);
+                    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c3) : "r"(o3), "r"(add3));
+                    atomicAdd(&s_pack[g], (1u << 18) + c1 * 64u + c3);
                 }
             }
         }
@@ -236,11 +239,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
         const uint32_t qh = pk & 63u;
         if (qh) atomicAdd(&acc[5 * M + col], (unsigned long long)qh);
     }
-    const double lm = warp_max((double)local_max), ln = warp_min((double)local_min);
-    if (lane == 0) {
-        if (lm > 0.0) atomicMax(p.range_bits, (unsigned long long)__double_as_longlong(lm));
-        if (ln < INFINITY) atomicMin(p.range_bits + 1, (unsigned long long)__double_as_longlong(ln));
-    }
+
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -507,7 +506,6 @@ void materialize(srb_mat *m, bool want_moments) {
         mm.exact_path = true;
         mm.acc = dev_zeros(s, sizeof(unsigned long long) * 6 * (M ? M : 1));
         mm.fexp = dev_alloc(s, sizeof(int));
-        new_absmax = new_range(s);
         SRB_LAUNCH(fexp_kernel, 1, 1, 0, s, bound->as<double>(), (int)(pending && m->pend_log1p), mm.fexp->as<int>());
         FusedParams p;
         p.off = st.offsets->as<int64_t>();
@@ -528,7 +526,6 @@ void materialize(srb_mat *m, bool want_moments) {
         p.rows_per_block = (uint32_t)rpb;
         p.fexp = mm.fexp->as<int>();
         p.acc = mm.acc->as<unsigned long long>();
-        p.range_bits = new_absmax->as<unsigned long long>();
         const uint64_t nb = (N + rpb - 1) / rpb;
         const unsigned grid = (unsigned)(nb * (uint64_t)S);
         const size_t smem = (size_t)W * 16;
@@ -598,7 +595,7 @@ void materialize(srb_mat *m, bool want_moments) {
         m->pend_log1p = false;
         m->pend_bound.reset();
         m->major = MajorStats();
-        m->absmax_all = new_absmax;  // exact path measured it; otherwise unknown (null)
+        m->absmax_all = new_absmax;  // unknown after a transform (null): recomputed by a K1 pass if ever needed
         m->minor = MinorMoments();
     }
     if (want_moments) m->minor = mm;

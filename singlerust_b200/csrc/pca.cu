@@ -367,7 +367,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     }
     SRB_TRACE("gram");
     if (c->nranks > 1) {
-        StageTimer t(c, ST_ALLREDUCE);
+        StageTimer t(c, ST_ALLREDUCE_GRAM);
         allreduce_f64_sum(c, G->as<double>(), (size_t)dpad * dpad);
     }
     // K8: correlation matrix + symmetric eigendecomposition
