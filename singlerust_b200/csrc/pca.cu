@@ -30,6 +30,16 @@ __global__ void lut_set_kernel(int *lut, const uint32_t *sel, uint64_t n_sel) {
     if (j < n_sel) atomicMax(&lut[sel[j]], (int)j);
 }
 
+// 16-bit LUT for the panel builder (60 KB at 30 k genes: stays in L1); 0xFFFF = not selected
+__global__ void lut16_kernel(const int *__restrict__ lut, uint16_t *__restrict__ lut16, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) lut16[i] = lut[i] < 0 ? (uint16_t)0xFFFF : (uint16_t)lut[i];
+}
+__global__ void shis_kernel(const float *__restrict__ shf, const float *__restrict__ isf, float2 *__restrict__ shis, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) shis[i] = make_float2(shf[i], isf[i]);
+}
+
 // reference-shaped dense block (parity/debug): all rows [row0,row0+nrows) x selection, f64 row-major
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_f64_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
@@ -69,8 +79,8 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
 // HBM: 8 B/nnz in, 4*dpad B/row out.
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
-                                                             const VT *__restrict__ val, const int *__restrict__ lut,
-                                                             const float *__restrict__ shf, const float *__restrict__ isf,
+                                                             const VT *__restrict__ val, const uint16_t *__restrict__ lut,
+                                                             const float2 *__restrict__ shis,
                                                              const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
                                                              uint64_t nrows, uint32_t dpad, __half *__restrict__ Xh,
                                                              __half *__restrict__ Xl) {
@@ -96,15 +106,16 @@ __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__re
                 cc[u] = in ? idx[k] : 0xFFFFFFFFu;
                 vv[u] = in ? (float)val[k] : 0.f;
             }
-            int pp[kBatch];
+            uint32_t pp[kBatch];
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) pp[u] = cc[u] != 0xFFFFFFFFu ? lut[cc[u]] : -1;
+            for (int u = 0; u < kBatch; ++u) pp[u] = cc[u] != 0xFFFFFFFFu ? (uint32_t)lut[cc[u]] : 0xFFFFu;
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
-                const int p = pp[u];
-                if (p >= 0) {
+                const uint32_t p = pp[u];
+                if (p != 0xFFFFu) {
                     // fp32 is enough here: the split keeps 22 bits of z, fp32 carries 24
-                    const float z = (vv[u] - shf[p]) * isf[p];
+                    const float2 si = shis[p];
+                    const float z = (vv[u] - si.x) * si.y;
                     const __half h = __float2half_rn(z);
                     rh[p] = h;
                     rl[p] = __float2half_rn(z - __half2float(h));
@@ -336,6 +347,10 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
                zc_h->as<__half>(), zc_l->as<__half>(), flag->as<uint32_t>());
 
     SRB_TRACE("lut + sel_stats");
+    SRB_REQUIRE(n_sel < 65535, SRB_ERR_UNSUPPORTED, "at most 65534 selected features");
+    Buf lut16 = dev_alloc(s, 2 * (M + 1)), shis = dev_alloc(s, 8 * dpad);
+    SRB_LAUNCH(lut16_kernel, nb(M), 256, 0, s, lut->as<int>(), lut16->as<uint16_t>(), M);
+    SRB_LAUNCH(shis_kernel, nb(dpad), 256, 0, s, shf->as<float>(), isf->as<float>(), shis->as<float2>(), dpad);
     // K6 panels
     Buf Xh = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad), Xl = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad);
     if (n) {
@@ -343,9 +358,9 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
         const size_t smem = 0;
         const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8 * 4);
         if (m->vdtype == SRB_F32) {
-            SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut->as<int>(), shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+            SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
-            SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut->as<int>(), shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+            SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         }
     }
     SRB_TRACE("panels alloc + densify enqueue");

@@ -396,3 +396,44 @@ def test_pca_tensor_core_gram_matches_fp64_and_oracle(ffi, ctx, n, m, n_top, k):
         assert cerr[j] <= RTOL, (j, cerr)
         assert serr[j] <= 10 * RTOL, (j, serr)
     assert good[:3].all()
+
+
+def test_full_size_config_L_properties(ffi, ctx):
+    """BASELINE.json configs[1]/[2] at FULL size (1M cells x 30k genes, ~1.5 G nnz) through size-independent properties:
+    count conservation, the reference's normalisation invariant, and the PCA identities
+    V^T V = I, scores^T scores = diag(lambda), lambda_j = evr_j * trace, trace = n*d for standardised columns."""
+    from singlerust_b200 import synth
+    n, m, d, k = 1_000_000, 30_000, 2000, 50
+    thr, amp = synth.gene_tables(m, seed=0x5EED0002, mean_density=0.05)
+    mat = ffi.DeviceMatrix.synth(ctx, 0x5EED0002, n, m, thr, amp)
+    nnz = mat.info()["nnz"]
+    assert 0.045 < nnz / (n * m) < 0.055
+    per_cell, per_gene = mat.number(ffi.ROW), mat.number(ffi.COLUMN)
+    assert int(per_cell.astype(np.uint64).sum()) == nnz == int(per_gene.astype(np.uint64).sum())   # bit-exact bookkeeping
+    raw_cell, raw_gene = mat.sum(ffi.ROW), mat.sum(ffi.COLUMN)
+    assert raw_cell.sum() == raw_gene.sum()                       # integer counts: both totals exact in f64
+    work = mat.clone()
+    work.normalize_total_inplace(1e4, ffi.ROW)
+    s = work.sum(ffi.ROW)
+    assert np.all(per_cell > 0)
+    np.testing.assert_allclose(s, 1e4, rtol=3e-7)                 # processing/mod.rs:451-462 invariant (f32 storage)
+    np.testing.assert_allclose(work.sum(ffi.COLUMN).sum(), 1e4 * n, rtol=1e-7)
+    np.testing.assert_array_equal(work.number(ffi.COLUMN), per_gene)   # the pattern is untouched
+    work.log1p_inplace()
+    gv = work.variance(ffi.COLUMN)
+    assert np.all(gv >= 0) and np.all(np.isfinite(gv))
+    sel = work.select_hvg(d)
+    assert len(set(sel.tolist())) == d
+    order = np.argsort(-gv, kind="stable")[:d]
+    np.testing.assert_array_equal(sel, order.astype(np.uint64))   # descending variance, ties by index
+    res = work.pca(sel, k)
+    V, S, evr = res["components"], res["scores"], res["explained_variance_ratio"]
+    np.testing.assert_allclose(V.T @ V, np.eye(k), atol=1e-9)
+    lam = evr * (n * d)                                           # trace(Z^T Z) = n * d when scale=True
+    G = S.T @ S
+    np.testing.assert_allclose(np.diag(G), lam, rtol=2e-5)
+    off = G - np.diag(np.diag(G))
+    assert np.max(np.abs(off)) <= 2e-5 * lam[0]
+    mean_err = np.max(np.abs(S.mean(axis=0)) / np.sqrt(lam / n))   # centred scores: column means ~ 0 (vs the column rms)
+    assert mean_err <= 2e-5, mean_err
+    assert np.all(np.diff(evr) <= 1e-12) and 0 < evr.sum() < 1
