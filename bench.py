@@ -253,12 +253,16 @@ def run_ours(args):
     run_steps(max(args.warmup, L))
     # untimed settling: lazily-loaded library modules (cuSOLVER) reach steady state at different speeds on a cold
     # box; keep stepping (at most 8 more rounds) until two consecutive rounds agree within 5 %
+    # (the stop decision is taken collectively: every rank must run the same number of steps, each has 2 allreduces)
     prev = None
     for _ in range(8):
         t0 = time.perf_counter()
         run_steps(L)
         dt = time.perf_counter() - t0
-        if prev is not None and abs(dt - prev) <= 0.05 * prev:
+        unsettled = torch.tensor([0.0 if (prev is not None and abs(dt - prev) <= 0.05 * prev) else 1.0], device=dev)
+        if world > 1:
+            dist.all_reduce(unsettled, op=dist.ReduceOp.MAX)
+        if float(unsettled.item()) == 0.0:
             break
         prev = dt
     barrier()
@@ -325,10 +329,15 @@ def run_ours(args):
 
     # ---- e2e: through the C ABI with HOST buffers (pinned), H2D + pipeline + D2H of the scores, every step ----
     if not args.no_e2e:
-        try:
+        if rank == 0:
+            print(json.dumps(dict(line, partial="main line before the e2e leg")), file=sys.stderr, flush=True)
+        if world == 1:
+            try:
+                line["e2e"] = run_e2e(args, ctx, mat, rank, world, dev, barrier)
+            except Exception as ex:  # never lose the main line
+                line["e2e"] = {"value": None, "unit": UNIT, "error": str(ex)[:300]}
+        else:
             line["e2e"] = run_e2e(args, ctx, mat, rank, world, dev, barrier)
-        except Exception as ex:  # never lose the main line
-            line["e2e"] = {"value": None, "unit": UNIT, "error": str(ex)[:300]}
     if rank == 0 and not args.no_cpu_baseline:
         try:
             sample = args.cpu_sample_cells or 16384
@@ -347,23 +356,46 @@ def run_ours(args):
 
 
 def run_e2e(args, ctx, mat, rank, world, dev, barrier):
+    """End to end through the C ABI with HOST buffers: every step uploads the rank's CSR from pinned host memory in the
+    reference's own layout (u64 offsets + u64 indices + f32 values), runs the pipeline and reads the scores back.
+    The pinned host copy is capped at ~40 GB per node, so at N >= 4 each rank uses the first 40 GB / (N * 18 KB) of its
+    cells (stated in the result). Every decision that could differ between ranks is agreed on with a collective first."""
     import psutil
     import torch
     import torch.distributed as dist
     from singlerust_b200 import _ffi
 
+    def agree_min(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t.item())
+
     info = mat.info()
-    n, nnz, k = info["nrows"], info["nnz"], min(args.pcs, args.hvg)
-    # host layout of the reference: usize (u64) offsets + indices, f32 values (nalgebra-sparse CsrMatrix<f32>)
-    need = 8 * (n + 1) + 12 * nnz + 8 * n * k
-    avail = psutil.virtual_memory().available / max(1, world)
-    if need * 1.3 > avail:
-        raise RuntimeError(f"host RAM too small for the e2e host copy: need {need/1e9:.1f} GB per rank, have {avail/1e9:.1f} GB")
-    off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
-    idx = torch.empty(nnz, dtype=torch.int64).pin_memory()
-    val = torch.empty(nnz, dtype=torch.float32).pin_memory()
-    scores = torch.empty((n, k), dtype=torch.float64).pin_memory()
-    _ffi.check(_ffi.lib().srb_mat_download(mat._h, _ffi._ptr(off), _ffi._ptr(idx), None, _ffi._ptr(val)))
+    n_full, nnz_full, k = info["nrows"], info["nnz"], min(args.pcs, args.hvg)
+    per_cell = 12.0 * nnz_full / max(1, n_full) + 8 * k + 8
+    budget = min(40e9, 0.5 * psutil.virtual_memory().available) / max(1, world)
+    n = int(agree_min(min(n_full, budget // per_cell)))
+    if n < 1024:
+        return {"value": None, "unit": UNIT, "skipped": "not enough host memory for a pinned copy of the input"}
+    # the e2e input: the first n cells of this rank's shard, regenerated on the device and copied to pinned host memory
+    from singlerust_b200 import synth
+    thr, amp = synth.gene_tables(args.genes, seed=SEED, mean_density=0.05)
+    src = mat if n == n_full else _ffi.DeviceMatrix.synth(ctx, SEED, n, args.genes, thr, amp, row0=rank * args.cells)
+    nnz = src.info()["nnz"]
+    ok = 1.0
+    try:
+        off = torch.empty(n + 1, dtype=torch.int64).pin_memory()
+        idx = torch.empty(nnz, dtype=torch.int64).pin_memory()
+        val = torch.empty(nnz, dtype=torch.float32).pin_memory()
+        scores = torch.empty((n, k), dtype=torch.float64).pin_memory()
+        _ffi.check(_ffi.lib().srb_mat_download(src._h, _ffi._ptr(off), _ffi._ptr(idx), None, _ffi._ptr(val)))
+    except Exception:
+        ok = 0.0
+    if agree_min(ok) < 1.0:
+        return {"value": None, "unit": UNIT, "skipped": "pinned host allocation failed on at least one rank"}
+    if src is not mat:
+        src.free()
 
     def step():
         m = _ffi.DeviceMatrix.upload(ctx, _ffi.CSR, n, args.genes, off, idx, val, nnz=nnz, idx_width=8, dtype=_ffi.F32)
@@ -371,7 +403,7 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
         m.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, scores_out=scores)
         m.free()
 
-    step()  # warm-up (allocations, pinned-path page faults)
+    step()  # warm-up (allocations, first touch of the pinned pages)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -387,7 +419,7 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
     h2d = 8 * (n + 1) + 12 * nnz
     d2h = 8 * n * k + 8 * min(args.hvg, args.genes) * (k + 1) + 8 * k
     return {"value": world * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ms_per_step": ms, "steps": args.e2e_steps,
+            "ms_per_step": ms, "steps": args.e2e_steps, "cells_per_gpu": n,
             "host_layout": "u64 offsets + u64 indices + f32 values in pinned memory (the Rust usize layout)"}
 
 
