@@ -100,9 +100,12 @@ struct srb_ctx {
     // stage timing
     cudaEvent_t ev0[srb::ST_COUNT] = {}, ev1[srb::ST_COUNT] = {};
     bool ev_used[srb::ST_COUNT] = {};
-    // cuSOLVER handle + workspace (lazy, eig.cu)
+    // cuSOLVER handle (lazy, eig.cu) and the high-priority side stream its small latency-bound kernels run on, so
+    // that they are scheduled ahead of another context's bandwidth-bound kernels when batches are pipelined
     void *solver = nullptr;
     void *solver_params = nullptr;
+    cudaStream_t eig_stream = nullptr;
+    cudaEvent_t eig_in = nullptr, eig_out = nullptr;
 };
 
 namespace srb {

@@ -23,23 +23,40 @@ void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals) {
         cusolverDnHandle_t h;
         SRB_CUSOLVER(cusolverDnCreate(&h));
         ctx->solver = h;
+        int lo = 0, hi = 0;
+        SRB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
+        SRB_CUDA(cudaStreamCreateWithPriority(&ctx->eig_stream, cudaStreamNonBlocking, hi));
+        SRB_CUDA(cudaEventCreateWithFlags(&ctx->eig_in, cudaEventDisableTiming));
+        SRB_CUDA(cudaEventCreateWithFlags(&ctx->eig_out, cudaEventDisableTiming));
     }
     cusolverDnHandle_t h = (cusolverDnHandle_t)ctx->solver;
-    SRB_CUSOLVER(cusolverDnSetStream(h, s));
+    cudaStream_t es = ctx->eig_stream;
+    SRB_CUSOLVER(cusolverDnSetStream(h, es));
     int lwork = 0;
     SRB_CUSOLVER(cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, d_evals, &lwork));
     Buf work = dev_alloc(s, sizeof(double) * (size_t)std::max(lwork, 1));
     Buf info = dev_zeros(s, sizeof(int));
+    // main stream -> eig stream (inputs ready, scratch buffers owned) ...
+    SRB_CUDA(cudaEventRecord(ctx->eig_in, s));
+    SRB_CUDA(cudaStreamWaitEvent(es, ctx->eig_in, 0));
     SRB_CUSOLVER(cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, d_evals, work->as<double>(), lwork, info->as<int>()));
     int hinfo = 0;
-    SRB_CUDA(cudaMemcpyAsync(&hinfo, info->p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    SRB_CUDA(cudaStreamSynchronize(s));
+    SRB_CUDA(cudaMemcpyAsync(&hinfo, info->p, sizeof(int), cudaMemcpyDeviceToHost, es));
+    // ... and back: everything enqueued on the main stream afterwards (including reuse of the scratch blocks through
+    // the block cache) is ordered after the eigensolver
+    SRB_CUDA(cudaEventRecord(ctx->eig_out, es));
+    SRB_CUDA(cudaStreamWaitEvent(s, ctx->eig_out, 0));
+    SRB_CUDA(cudaStreamSynchronize(es));
     SRB_REQUIRE(hinfo == 0, SRB_ERR_NAN, "syevd did not converge / illegal value (info=" + std::to_string(hinfo) + "): NaN in the correlation matrix?");
 }
 
 void eig_destroy(srb_ctx *ctx) {
     if (ctx->solver) cusolverDnDestroy((cusolverDnHandle_t)ctx->solver);
     ctx->solver = nullptr;
+    if (ctx->eig_stream) cudaStreamDestroy(ctx->eig_stream);
+    if (ctx->eig_in) cudaEventDestroy(ctx->eig_in);
+    if (ctx->eig_out) cudaEventDestroy(ctx->eig_out);
+    ctx->eig_stream = nullptr, ctx->eig_in = nullptr, ctx->eig_out = nullptr;
 }
 
 }  // namespace srb
