@@ -649,9 +649,13 @@ int32_t srb_densify_selected(srb_mat *m, const uint64_t *col_sel, uint64_t n_sel
     SRB_API_BEGIN
     check_mat(m);
     SRB_REQUIRE(out || n_sel == 0 || m->nrows == 0, SRB_ERR_INVALID_ARG, "out is null");
-    SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "selected densify is implemented for CSR storage");
     srb_ctx *c = m->ctx;
     SRB_CUDA(cudaSetDevice(c->device));
+    std::unique_ptr<srb_mat> twin;  // convert_to_array_f64_csc_selected (shared/mod.rs:261-290): via a CSR twin
+    if (m->format == SRB_CSC) {
+        twin.reset(csc_to_csr(m));
+        m = twin.get();
+    }
     Buf d_sel = upload_selection(m, col_sel, n_sel);
     if (n_sel == 0 || m->nrows == 0) return SRB_OK;
     const uint64_t rows_per = std::max<uint64_t>(1, std::min<uint64_t>(m->nrows, (1ull << 27) / n_sel));
@@ -673,11 +677,15 @@ int32_t srb_pca(srb_mat *m, const uint64_t *col_sel, uint64_t n_sel, uint64_t k,
                 int32_t gram_mode, double *scores, double *components, double *explained_variance_ratio) {
     SRB_API_BEGIN
     check_mat(m);
-    SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "PCA is implemented for CSR storage (cells = rows)");
     SRB_REQUIRE(n_sel >= 1 && k >= 1, SRB_ERR_INVALID_ARG, "need at least one feature and one component");
     srb_ctx *c = m->ctx;
     SRB_CUDA(cudaSetDevice(c->device));
     reset_stage_timers(c);
+    std::unique_ptr<srb_mat> twin;  // CSC-stored X: PCA runs on a CSR twin (cells = rows)
+    if (m->format == SRB_CSC) {
+        twin.reset(csc_to_csr(m));
+        m = twin.get();
+    }
     Buf d_sel = upload_selection(m, col_sel, n_sel);
     PcaOut o{scores, components, explained_variance_ratio};
     pca_run(m, d_sel->as<uint32_t>(), n_sel, std::min<uint64_t>(k, n_sel), center != 0, scale != 0, gram_mode, o);
@@ -689,7 +697,6 @@ int32_t srb_pipeline_normalize_hvg_pca(srb_mat *m, double target_sum, uint64_t n
                                        double *components, double *explained_variance_ratio) {
     SRB_API_BEGIN
     check_mat(m);
-    SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "pipeline is implemented for CSR storage (cells = rows)");
     SRB_REQUIRE(n_top >= 1 && k >= 1, SRB_ERR_INVALID_ARG, "need at least one feature and one component");
     srb_ctx *c = m->ctx;
     SRB_CUDA(cudaSetDevice(c->device));
@@ -712,6 +719,11 @@ int32_t srb_pipeline_normalize_hvg_pca(srb_mat *m, double target_sum, uint64_t n
         for (uint64_t i = 0; i < n_sel; ++i) hvg_out[i] = h[i];
     }
     PcaOut o{scores, components, explained_variance_ratio};
+    std::unique_ptr<srb_mat> twin;
+    if (m->format == SRB_CSC) {
+        twin.reset(csc_to_csr(m));
+        m = twin.get();
+    }
     pca_run(m, d_idx->as<uint32_t>(), n_sel, std::min<uint64_t>(k, n_sel), center != 0, scale != 0, gram_mode, o);
     SRB_API_END
 }

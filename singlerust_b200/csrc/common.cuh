@@ -206,6 +206,8 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
 void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G);
 void scores_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, const double *W,
                     uint32_t kpad, uint32_t k, double *scores);
+// convert.cu
+srb_mat *csc_to_csr(srb_mat *m);
 // eig.cu
 void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals_desc_out);  // C overwritten by eigenvectors
 // comm.cu

@@ -437,3 +437,28 @@ def test_full_size_config_L_properties(ffi, ctx):
     mean_err = np.max(np.abs(S.mean(axis=0)) / np.sqrt(lam / n))   # centred scores: column means ~ 0 (vs the column rms)
     assert mean_err <= 2e-5, mean_err
     assert np.all(np.diff(evr) <= 1e-12) and 0 < evr.sum() < 1
+
+
+def test_csc_densify_and_pca_match_csr_and_oracle(ffi, ctx_faithful):
+    """CSC-stored X (csc.rs / convert_to_array_f64_csc_selected, shared/mod.rs:261-290): same dense block and PCA as CSR."""
+    rng = np.random.default_rng(41)
+    a = clustered_counts(rng, 1500, 260)
+    ac = a.tocsc()
+    ac.sort_indices()
+    mr, mc = upload(ffi, ctx_faithful, a), upload(ffi, ctx_faithful, ac)
+    oc = O.Compressed.from_scipy(ac)
+    for mm in (mr, mc):
+        mm.normalize_total_inplace(1e4, ffi.ROW)
+        mm.log1p_inplace()
+    ocl = O.log1p(O.normalize_total(oc, 1e4, O.ROW))
+    sel_r, sel_c = mr.select_hvg(40), mc.select_hvg(40)
+    # CSC/Column variance is the two-pass major form (csc.rs:161-173); same ranking on this data as the oracle's
+    np.testing.assert_array_equal(sel_c, O.select_hvg(O.variance(ocl, O.COLUMN), 40))
+    dc = mc.densify_selected(sel_c)
+    np.testing.assert_allclose(dc, O.densify_selected(ocl, np.arange(1500), sel_c), rtol=1e-13)
+    np.testing.assert_allclose(dc, mr.densify_selected(sel_c), rtol=1e-13)
+    rc, rr = mc.pca(sel_c, 6, gram_mode=ffi.GRAM_FP64), mr.pca(sel_c, 6, gram_mode=ffi.GRAM_FP64)
+    np.testing.assert_allclose(rc["explained_variance_ratio"], rr["explained_variance_ratio"], rtol=1e-10)
+    np.testing.assert_allclose(sign_align(rc["scores"], rr["scores"]), rr["scores"], atol=1e-7)
+    want = P.pca_pipeline(ocl, 40, 6, selection=sel_c)
+    np.testing.assert_allclose(rc["explained_variance_ratio"], want["explained_variance_ratio"], rtol=RTOL)
