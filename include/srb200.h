@@ -134,6 +134,12 @@ int32_t srb_stream_push(srb_stream *s, uint64_t nmajor_chunk, uint64_t nnz, cons
 int32_t srb_stream_number(srb_stream *s, int32_t direction, uint32_t *out);
 int32_t srb_stream_sum(srb_stream *s, int32_t direction, double *out);
 int32_t srb_stream_variance(srb_stream *s, int32_t direction, double *out); /* new: not in the reference */
+/* Residency (new): keep the pushed chunks on the device as one matrix, so a backed data set that fits
+ * the GPUs' HBM (180 GB each; ~6 M cells of 1500 nnz per GPU) is uploaded once, chunk by chunk, and then runs the same
+ * normalise / HVG / PCA kernels as an in-memory matrix. Call before the first push; nnz_hint = 0 grows geometrically.
+ * keep_statistics = 0 skips the per-chunk accumulators above. srb_stream_finish_matrix hands the matrix over. */
+int32_t srb_stream_set_retain(srb_stream *s, uint64_t nnz_hint, int32_t keep_statistics);
+int32_t srb_stream_finish_matrix(srb_stream *s, srb_mat **out);
 int32_t srb_stream_free(srb_stream *s);
 
 /* ---- normalisation / transform -------------------------------------------------------------------- */

@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
             "srb_stream_number": [vp, i32, vp],
             "srb_stream_sum": [vp, i32, vp],
             "srb_stream_variance": [vp, i32, vp],
+            "srb_stream_set_retain": [vp, u64, i32],
+            "srb_stream_finish_matrix": [vp, C.POINTER(vp)],
             "srb_stream_free": [vp],
             "srb_normalize_total_inplace": [vp, f64, i32],
             "srb_log1p_inplace": [vp],
@@ -353,6 +355,14 @@ class ChunkStream:
         values = np.ascontiguousarray(values)
         check(lib().srb_stream_push(self._h, offsets.size - 1, int(offsets[-1]), _ptr(offsets), _ptr(indices), 8,
                                     _ptr(values), DTYPES[values.dtype]))
+
+    def set_retain(self, nnz_hint=0, keep_statistics=True):
+        check(lib().srb_stream_set_retain(self._h, nnz_hint, int(keep_statistics)))
+
+    def finish_matrix(self) -> "DeviceMatrix":
+        h = C.c_void_p()
+        check(lib().srb_stream_finish_matrix(self._h, C.byref(h)))
+        return DeviceMatrix(self.ctx, h)
 
     def _len(self, direction):
         return self.nrows if direction == ROW else self.ncols

@@ -1,2 +1,2 @@
 """Mirror of the reference's src/backed front-end (out-of-core data)."""
-from . import statistics  # noqa: F401
+from . import processing, statistics  # noqa: F401

@@ -127,3 +127,29 @@ def test_two_gpu_row_sharding_matches_single_gpu():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU OK" in r.stdout
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_backed_chunked_pipeline_equals_in_memory(env, fmt):
+    """BASELINE config 5 in miniature: chunk-streamed (resident) X gives bit-identical statistics and the same PCA as
+    the whole-matrix upload; chunk boundaries must not matter."""
+    from tests.test_gpu_parity import clustered_counts
+    D, CM, FS, mem, backed = env["Direction"], env["ComputationMode"], env["FeatureSelection"], env["memory"], env["backed"]
+    a = clustered_counts(np.random.default_rng(12), 1700, 240)
+    src = a if fmt == "csr" else a.tocsc()
+    whole = env["IMAnnData"].from_scipy(env["ctx"], src)
+    b = env["BackedAnnData"](src)
+    for chunk in (1, 333, 5000):
+        dev = backed.processing.load_resident(env["ctx"], b, CM.Chunked(chunk))
+        off, idx, val = dev.x().download()
+        off0, idx0, val0 = whole.x().download()
+        np.testing.assert_array_equal(off, off0)
+        np.testing.assert_array_equal(idx, idx0)
+        np.testing.assert_array_equal(val, val0)
+    res = backed.processing.normalize_hvg_pca(env["ctx"], b, CM.Chunked(400), 1e4, 30, 5)
+    ref = whole.deep_clone()
+    mem.processing.normalize_total_inplace(ref, 1e4, D.Row)
+    mem.processing.log1p_transform_inplace(ref)
+    mem.processing.pca_inplace(ref, 5, True, True, None, FS.HighlyVariable(30))
+    np.testing.assert_allclose(res.explained_variance_ratio, ref.explained_variance_ratio, rtol=1e-9)
+    np.testing.assert_allclose(sign_align(res.obsm["X_pca"], ref.obsm["X_pca"]), ref.obsm["X_pca"], atol=1e-6)
