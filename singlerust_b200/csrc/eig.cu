@@ -4,6 +4,9 @@
 // step that is not on the HBM/tensor hot path).
 #include <cusolverDn.h>
 
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 namespace srb {
@@ -32,14 +35,38 @@ void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals) {
     cusolverDnHandle_t h = (cusolverDnHandle_t)ctx->solver;
     cudaStream_t es = ctx->eig_stream;
     SRB_CUSOLVER(cusolverDnSetStream(h, es));
-    int lwork = 0;
-    SRB_CUSOLVER(cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, d_evals, &lwork));
-    Buf work = dev_alloc(s, sizeof(double) * (size_t)std::max(lwork, 1));
+    static int use_x = -1;  // SRB_EIG_X=1: the 64-bit generic API (cusolverDnXsyevd) instead of the legacy Dsyevd
+    if (use_x < 0) {
+        const char *e = getenv("SRB_EIG_X");
+        use_x = (e && e[0] == '1') ? 1 : 0;
+    }
     Buf info = dev_zeros(s, sizeof(int));
+    Buf work;
+    int lwork = 0;
+    size_t wdev = 0, whost = 0;
+    std::vector<char> hwork;
+    if (!ctx->solver_params) {
+        cusolverDnParams_t prm;
+        SRB_CUSOLVER(cusolverDnCreateParams(&prm));
+        ctx->solver_params = prm;
+    }
+    if (use_x) {
+        SRB_CUSOLVER(cusolverDnXsyevd_bufferSize(h, (cusolverDnParams_t)ctx->solver_params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER,
+                                                 (int64_t)d, CUDA_R_64F, d_C, (int64_t)d, CUDA_R_64F, d_evals, CUDA_R_64F, &wdev, &whost));
+        work = dev_alloc(s, std::max<size_t>(wdev, 16));
+        hwork.resize(std::max<size_t>(whost, 16));
+    } else {
+        SRB_CUSOLVER(cusolverDnDsyevd_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, d_evals, &lwork));
+        work = dev_alloc(s, sizeof(double) * (size_t)std::max(lwork, 1));
+    }
     // main stream -> eig stream (inputs ready, scratch buffers owned) ...
     SRB_CUDA(cudaEventRecord(ctx->eig_in, s));
     SRB_CUDA(cudaStreamWaitEvent(es, ctx->eig_in, 0));
-    SRB_CUSOLVER(cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, d_evals, work->as<double>(), lwork, info->as<int>()));
+    if (use_x)
+        SRB_CUSOLVER(cusolverDnXsyevd(h, (cusolverDnParams_t)ctx->solver_params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int64_t)d,
+                                      CUDA_R_64F, d_C, (int64_t)d, CUDA_R_64F, d_evals, CUDA_R_64F, work->p, wdev, hwork.data(), whost, info->as<int>()));
+    else
+        SRB_CUSOLVER(cusolverDnDsyevd(h, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, d_evals, work->as<double>(), lwork, info->as<int>()));
     int hinfo = 0;
     SRB_CUDA(cudaMemcpyAsync(&hinfo, info->p, sizeof(int), cudaMemcpyDeviceToHost, es));
     // ... and back: everything enqueued on the main stream afterwards (including reuse of the scratch blocks through
@@ -51,6 +78,8 @@ void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals) {
 }
 
 void eig_destroy(srb_ctx *ctx) {
+    if (ctx->solver_params) cusolverDnDestroyParams((cusolverDnParams_t)ctx->solver_params);
+    ctx->solver_params = nullptr;
     if (ctx->solver) cusolverDnDestroy((cusolverDnHandle_t)ctx->solver);
     ctx->solver = nullptr;
     if (ctx->eig_stream) cudaStreamDestroy(ctx->eig_stream);

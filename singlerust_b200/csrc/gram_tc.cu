@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -292,9 +293,24 @@ static CUtensorMap panel_map(const __half *X, uint64_t n, uint32_t dpad) {
 
 }  // namespace tc
 
+CUtensorMap gram_panel_map(const __half *X, uint64_t n, uint32_t dpad) { return tc::panel_map(X, n, dpad); }
+void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G);  // gram_tc2.cu
+
 void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G) {
     using namespace tc;
     if (n == 0) return;
+    {
+        // CTA-pair kernel (cta_group::2) unless SRB_GRAM_PAIR=0
+        static int use_pair = -1;
+        if (use_pair < 0) {
+            const char *e = getenv("SRB_GRAM_PAIR");
+            use_pair = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (use_pair) {
+            gram_tcgen05_pair(ctx, Xh, Xl, n, dpad, G);
+            return;
+        }
+    }
     cudaStream_t s = ctx->stream;
     SRB_REQUIRE(dpad % BN == 0, SRB_ERR_INVALID_ARG, "dpad must be a multiple of 256");
     const uint32_t NI = dpad / BM, NJ = dpad / BN;
