@@ -99,6 +99,11 @@ int32_t srb_mat_info(srb_mat *m, uint64_t *nrows, uint64_t *ncols, uint64_t *nnz
 /* current values as f64 (what the reference holds after normalise) or f32; any of the pointers may be NULL */
 int32_t srb_mat_download(srb_mat *m, uint64_t *offsets, uint64_t *indices, double *values_f64, float *values_f32);
 
+/* Row / column subset (new device op for SURVEY §8f N2): the IMAnnData::subset step of filter_cells / filter_genes
+ * (src/memory/processing/mod.rs:86-146, 245-299). keep_rows[nrows] / keep_cols[ncols] are host byte masks (non-zero =
+ * keep; NULL = keep all). Produces a new compacted matrix (indices renumbered); the input is left untouched. */
+int32_t srb_mat_subset(srb_mat *m, const uint8_t *keep_rows, const uint8_t *keep_cols, srb_mat **out);
+
 /* synthetic count matrix generated on the device (bit-identical to oracle/srb_oracle.c
  * orc_synth_*): rows [row0, row0+nrows) of the global matrix for `seed`; thr/amp are host tables of ncols. */
 int32_t srb_synth_csr(srb_ctx *ctx, uint32_t seed, int32_t skew, uint64_t row0, uint64_t nrows, uint32_t ncols,

@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
             "srb_mat_set_shard": [vp, u64, u64],
             "srb_mat_free": [vp],
             "srb_mat_clone": [vp, C.POINTER(vp)],
+            "srb_mat_subset": [vp, vp, vp, C.POINTER(vp)],
             "srb_mat_info": [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(i32), C.POINTER(i32)],
             "srb_mat_download": [vp, vp, vp, vp, vp],
             "srb_synth_csr": [vp, C.c_uint32, i32, u64, u64, C.c_uint32, vp, vp, C.POINTER(vp)],
@@ -216,6 +217,17 @@ class DeviceMatrix:
     def clone(self):
         h = C.c_void_p()
         check(lib().srb_mat_clone(self._h, C.byref(h)))
+        return DeviceMatrix(self.ctx, h)
+
+    def subset(self, keep_rows=None, keep_cols=None):
+        """Row / column compaction (IMAnnData::subset): boolean masks, None = keep all."""
+        kr = None if keep_rows is None else np.ascontiguousarray(keep_rows, np.uint8)
+        kc = None if keep_cols is None else np.ascontiguousarray(keep_cols, np.uint8)
+        nr, nc = self.shape
+        assert kr is None or kr.size == nr
+        assert kc is None or kc.size == nc
+        h = C.c_void_p()
+        check(lib().srb_mat_subset(self._h, _ptr(kr), _ptr(kc), C.byref(h)))
         return DeviceMatrix(self.ctx, h)
 
     def free(self):

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsrb200.so")
 SOURCES = ["api.cu", "major_stats.cu", "minor_moments.cu", "select.cu", "pca.cu", "gram_tc.cu", "gram_tc2.cu", "eig.cu", "comm.cu",
-           "synth.cu", "stream.cu", "convert.cu"]
+           "synth.cu", "stream.cu", "convert.cu", "subset.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -8,6 +8,78 @@ from ..anndata import IMAnnData
 from ..shared import Direction, FeatureSelection
 
 
+# ---- filters: memory/processing/mod.rs:16-299 ---------------------------------------------------------
+F64_MIN, F64_MAX = -np.finfo(np.float64).max, np.finfo(np.float64).max
+
+
+def calculate_percentiles(values, lower_lim, upper_lim):
+    """processing/mod.rs:148-174: ndarray-stats quantile with Linear interpolation (= NumPy's default 'linear');
+    f64::MIN / f64::MAX when the limit is not Relative."""
+    v = np.asarray(values, dtype=np.float64)
+    if np.isnan(v).any():
+        raise ValueError("NaN in the per-line sums (noisy_float n64 panics in the reference)")
+    lo = float(np.quantile(v, lower_lim.value)) if lower_lim.is_relative() else F64_MIN
+    hi = float(np.quantile(v, upper_lim.value)) if upper_lim.is_relative() else F64_MAX
+    return lo, hi
+
+
+def create_filter_mask(n, counts, sums, lower_lim, upper_lim, lower_percentile, upper_percentile):
+    """processing/mod.rs:32-83 (cells) and :193-243 (genes): the nine (lower, upper) FlexValue combinations.
+    Absolute limits compare the stored-entry COUNT, Relative limits compare the SUM against its percentile."""
+    keep = np.ones(n, dtype=bool)
+    if lower_lim.is_absolute():
+        keep &= counts >= lower_lim.value
+    elif lower_lim.is_relative():
+        keep &= sums >= lower_percentile
+    if upper_lim.is_absolute():
+        keep &= counts <= upper_lim.value
+    elif upper_lim.is_relative():
+        keep &= sums <= upper_percentile
+    return keep
+
+
+def _filter(adata: IMAnnData, lower_lim, upper_lim, direction: Direction, inplace: bool):
+    need_count = lower_lim.is_absolute() or upper_lim.is_absolute()
+    counts = adata.x().number(int(direction)) if need_count else None        # calculate_{cell,gene}_stats :16-30, :176-191
+    sums = adata.x().sum(int(direction))
+    lo, hi = calculate_percentiles(sums, lower_lim, upper_lim)
+    n = adata.n_obs if direction == Direction.Row else adata.n_vars
+    mask = create_filter_mask(n, counts, sums, lower_lim, upper_lim, lo, hi)
+    new_x = adata.x().subset(mask, None) if direction == Direction.Row else adata.x().subset(None, mask)
+    side = "obs" if direction == Direction.Row else "var"
+    new_cols = {k: np.asarray(v)[mask] for k, v in getattr(adata, side).items()}
+    if inplace:
+        adata._x = new_x
+        setattr(adata, side, new_cols)
+        if direction == Direction.Row:
+            adata.obsm = {k: np.asarray(v)[mask] for k, v in adata.obsm.items()}
+        else:
+            adata.varm = {k: np.asarray(v)[mask] for k, v in adata.varm.items()}
+        return None
+    out = IMAnnData(new_x, new_cols if side == "obs" else dict(adata.obs), new_cols if side == "var" else dict(adata.var))
+    return out
+
+
+def filter_cells_inplace(adata: IMAnnData, lower_lim, upper_lim) -> None:
+    """processing/mod.rs:86-121."""
+    _filter(adata, lower_lim, upper_lim, Direction.Row, True)
+
+
+def filter_cells(adata: IMAnnData, lower_lim, upper_lim) -> IMAnnData:
+    """processing/mod.rs:123-146."""
+    return _filter(adata, lower_lim, upper_lim, Direction.Row, False)
+
+
+def filter_genes_inplace(adata: IMAnnData, lower_lim, upper_lim) -> None:
+    """processing/mod.rs:245-271."""
+    _filter(adata, lower_lim, upper_lim, Direction.Column, True)
+
+
+def filter_genes(adata: IMAnnData, lower_lim, upper_lim) -> IMAnnData:
+    """processing/mod.rs:273-299."""
+    return _filter(adata, lower_lim, upper_lim, Direction.Column, False)
+
+
 def normalize_total_inplace(adata: IMAnnData, target_sum: float, direction: Direction) -> None:
     """processing/mod.rs:303-312 -> scale::scale_row / scale_col (scale/mod.rs:7-173)."""
     adata.x().normalize_total_inplace(target_sum, int(direction))

@@ -153,3 +153,54 @@ def test_backed_chunked_pipeline_equals_in_memory(env, fmt):
     mem.processing.pca_inplace(ref, 5, True, True, None, FS.HighlyVariable(30))
     np.testing.assert_allclose(res.explained_variance_ratio, ref.explained_variance_ratio, rtol=1e-9)
     np.testing.assert_allclose(sign_align(res.obsm["X_pca"], ref.obsm["X_pca"]), ref.obsm["X_pca"], atol=1e-6)
+
+
+LIMS = [("Absolute", 12), ("Relative", 0.2), ("None", None)]
+UPS = [("Absolute", 30), ("Relative", 0.9), ("None", None)]
+
+
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_filter_cells_and_genes_all_flexvalue_arms(env, fmt):
+    """filter_cells / filter_genes (processing/mod.rs:86-146, 245-299) for all nine FlexValue combinations: the mask
+    and the compacted matrix are bit-identical to the oracle's; plus the reference's own assertion (fewer lines)."""
+    from oracle import filter_oracle as FO
+    from singlerust_b200.shared import FlexValue
+    mem = env["memory"]
+    a = random_csr(np.random.default_rng(17), 400, 90, 0.25, dtype=np.float32, empty_rows=(3,), empty_cols=(8,))
+    src = a if fmt == "csr" else a.tocsc()
+
+    def fv(t):
+        return {"Absolute": FlexValue.Absolute, "Relative": FlexValue.Relative}[t[0]](t[1]) if t[0] != "None" else FlexValue.None_()
+
+    for lo in LIMS:
+        for up in UPS:
+            for axis, fn in ((0, mem.processing.filter_cells), (1, mem.processing.filter_genes)):
+                lo_a, up_a = lo, up
+                if axis == 1 and lo[0] == "Absolute":
+                    lo_a, up_a = ("Absolute", 80), (up if up[0] != "Absolute" else ("Absolute", 120))
+                adata = env["IMAnnData"].from_scipy(env["ctx"], src)
+                adata.obs["tag"] = np.arange(400)
+                adata.var["tag"] = np.arange(90)
+                got = fn(adata, fv(lo_a), fv(up_a))
+                want, m = FO.filter_matrix(a, lo_a, up_a, axis)
+                off, idx, val = got.x().download()
+                w = want if fmt == "csr" else want.tocsc()
+                w.sort_indices()
+                assert got.x().shape == want.shape
+                np.testing.assert_array_equal(off, w.indptr)
+                np.testing.assert_array_equal(idx, w.indices)
+                np.testing.assert_array_equal(val, w.data)
+                tags = got.obs["tag"] if axis == 0 else got.var["tag"]
+                np.testing.assert_array_equal(tags, np.nonzero(m)[0])
+                assert adata.x().shape == (400, 90)          # non-inplace leaves the input untouched
+    # the reference's own tests (processing/mod.rs:385-417): filtered count < original, Absolute and Relative limits
+    adata = env["IMAnnData"].from_scipy(env["ctx"], src)
+    n0 = adata.n_obs
+    mem.processing.filter_cells_inplace(adata, FlexValue.Absolute(20), FlexValue.None_())
+    assert adata.n_obs < n0
+    g0 = adata.n_vars
+    mem.processing.filter_genes_inplace(adata, FlexValue.Relative(0.1), FlexValue.Relative(0.9))
+    assert adata.n_vars < g0
+    # statistics keep working on the compacted matrix
+    off, idx, val = adata.x().download()
+    assert np.array_equal(adata.x().number(0), np.diff(off.astype(np.int64)) if fmt == "csr" else np.bincount(idx.astype(np.int64), minlength=adata.n_obs))

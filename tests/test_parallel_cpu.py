@@ -125,3 +125,25 @@ def test_sharded_gene_moments_are_bit_identical_and_match_oracle():
     ex2 = sq1 / np.maximum(cnt1, 1)
     # backward-error bound of f32 storage: |dvar| <= 1e-5 var + 4e-7 E[x^2]
     assert np.all(np.abs(var1 - want) <= 1e-5 * want + 4e-7 * ex2)
+
+
+def test_filter_mask_host_logic_matches_oracle_all_nine_arms():
+    """create_filter_mask / calculate_percentiles (processing/mod.rs:32-83, 148-174): host logic vs the arm-by-arm oracle."""
+    from oracle import filter_oracle as FO
+    from singlerust_b200.memory.processing import calculate_percentiles, create_filter_mask
+    from singlerust_b200.shared import FlexValue
+    rng = np.random.default_rng(5)
+    counts = rng.integers(0, 60, size=500).astype(np.uint32)
+    sums = rng.uniform(0, 1000, size=500)
+    np.testing.assert_allclose(FO.linear_quantile(sums, 0.37), np.quantile(sums, 0.37), rtol=1e-15)
+
+    def fv(t):
+        return {"Absolute": FlexValue.Absolute, "Relative": FlexValue.Relative}[t[0]](t[1]) if t[0] != "None" else FlexValue.None_()
+
+    for lo in (("Absolute", 10), ("Relative", 0.25), ("None", None)):
+        for up in (("Absolute", 45), ("Relative", 0.8), ("None", None)):
+            lp, upc = calculate_percentiles(sums, fv(lo), fv(up))
+            got = create_filter_mask(500, counts, sums, fv(lo), fv(up), lp, upc)
+            np.testing.assert_array_equal(got, FO.mask(counts, sums, lo, up))
+    with pytest.raises(ValueError):
+        calculate_percentiles(np.array([1.0, np.nan]), FlexValue.Relative(0.5), FlexValue.None_())
