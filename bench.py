@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--clock-period-ms", type=int, default=200, help="nvidia-smi sampling period; 0 disables the sampler")
+    ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period; 0 disables the sampler")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--cpu-sample-cells", type=int, default=0, help="0 = auto")
     return ap.parse_args()
