@@ -91,8 +91,9 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
                        int32_t dtype, srb_mat **out);
 int32_t srb_mat_set_shard(srb_mat *m, uint64_t global_row0, uint64_t global_nrows);
 int32_t srb_mat_free(srb_mat *m);
-/* deep copy (IMAnnData::deep_clone used by normalize_total / log1p_transform, processing/mod.rs:314-332);
- * the index structure is shared (immutable), values are copied */
+/* deep copy semantics (IMAnnData::deep_clone used by normalize_total / log1p_transform, processing/mod.rs:314-332),
+ * implemented copy-on-write: the index structure (immutable) and the value buffer are shared until one side is
+ * transformed, which then writes into a fresh buffer */
 int32_t srb_mat_clone(srb_mat *m, srb_mat **out);
 int32_t srb_mat_info(srb_mat *m, uint64_t *nrows, uint64_t *ncols, uint64_t *nnz, int32_t *format,
                      int32_t *value_dtype /* SRB_F32 or SRB_F64: current device storage */);

@@ -232,10 +232,6 @@ __global__ void sqrt_kernel(double *a, uint64_t n) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = sqrt(a[i]);
 }
-__global__ void any_nan_kernel(const double *a, uint64_t n, uint32_t *flag) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && a[i] != a[i]) atomicOr(flag, 1u);
-}
 
 static unsigned nb(uint64_t n) { return (unsigned)std::max<uint64_t>(1, (n + 255) / 256); }
 

@@ -124,9 +124,9 @@ struct Structure {
 struct MinorMoments {
     bool valid = false;
     bool exact_path = false;  // fixed-point SMEM path (true) or fp64 global-atomic path (false)
-    Buf acc;                  // u64[5 * nminor]: cnt, sum, sqA, sqB, sqC   (exact path, after allreduce = global)
+    Buf acc;                  // u64[6 * nminor]: cnt, sumA, sumB, sqA, sqB, sqC (32-bit limbs; after allreduce = global)
     Buf fexp;                 // int32[1]: F (power-of-two scale), device-resident
-    Buf cnt, sum, sq;         // finalised: u32[nminor] (local rows only if not reduced), f64[nminor], f64[nminor]
+    Buf cnt, sum, sq;         // finalised f64[nminor] each (counts are exact integers in f64)
     bool reduced = false;     // allreduced over ranks
 };
 

@@ -12,6 +12,7 @@
 //   scores = Z V_k                                                          (pca/mod.rs:156-185)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -121,6 +122,66 @@ __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__re
                     rl[p] = __float2half_rn(z - __half2float(h));
                 }
             }
+        }
+        __syncwarp();
+    }
+}
+
+// default variant: register double buffer (SRB_DENSIFY_PIPE=0 selects the plain batched kernel above)
+template <typename VT>
+__global__ void __launch_bounds__(256) densify_panels_pipe_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
+                                                             const VT *__restrict__ val, const uint16_t *__restrict__ lut,
+                                                             const float2 *__restrict__ shis,
+                                                             const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
+                                                             uint64_t nrows, uint32_t dpad, __half *__restrict__ Xh,
+                                                             __half *__restrict__ Xl) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    const uint32_t nvec = dpad / 8;  // uint4 = 8 halves
+    const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
+    constexpr int kBatch = 4;
+    for (uint64_t r = warp; r < nrows; r += nwarps) {
+        const int64_t a = off[r], b = off[r + 1];
+        uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
+        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
+        __syncwarp();
+        __half *rh = Xh + r * dpad, *rl = Xl + r * dpad;
+        // software pipeline: the next batch of (index, value) loads is in flight while the current batch walks the
+        // dependent chain index -> LUT -> (shift, 1/sd) -> store
+        uint32_t cc[kBatch], cn[kBatch];
+        float vv[kBatch], vn[kBatch];
+        int64_t k0 = a + lane;
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int64_t k = k0 + 32 * u;
+            cc[u] = k < b ? idx[k] : 0xFFFFFFFFu;
+            vv[u] = k < b ? (float)val[k] : 0.f;
+        }
+        for (; k0 < b; k0 += 32 * kBatch) {
+            const int64_t kn = k0 + 32 * kBatch;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int64_t k = kn + 32 * u;
+                cn[u] = k < b ? idx[k] : 0xFFFFFFFFu;
+                vn[u] = k < b ? (float)val[k] : 0.f;
+            }
+            uint32_t pp[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) pp[u] = cc[u] != 0xFFFFFFFFu ? (uint32_t)lut[cc[u]] : 0xFFFFu;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const uint32_t p = pp[u];
+                if (p != 0xFFFFu) {
+                    const float2 si = shis[p];
+                    const float z = (vv[u] - si.x) * si.y;
+                    const __half h = __float2half_rn(z);
+                    rh[p] = h;
+                    rl[p] = __float2half_rn(z - __half2float(h));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) cc[u] = cn[u], vv[u] = vn[u];
         }
         __syncwarp();
     }
@@ -357,7 +418,14 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
         StageTimer t(c, ST_DENSIFY);
         const size_t smem = 0;
         const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8 * 4);
-        if (m->vdtype == SRB_F32) {
+        static int pipe = -1;
+        if (pipe < 0) {
+            const char *e = getenv("SRB_DENSIFY_PIPE");
+            pipe = (e && e[0] == '0') ? 0 : 1;  // default: register double-buffered variant (4.40 vs 4.68 ms at L)
+        }
+        if (m->vdtype == SRB_F32 && pipe) {
+            SRB_LAUNCH((densify_panels_pipe_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        } else if (m->vdtype == SRB_F32) {
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
             SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
