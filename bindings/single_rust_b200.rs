@@ -1,0 +1,69 @@
+// single_rust_b200.rs — UNCOMPILED mirror of include/srb200.h for the reference crate (no Rust toolchain exists in the
+// build image). Drop into src/b200/sys.rs and link with `cargo:rustc-link-lib=dylib=srb200`.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)] pub struct srb_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct srb_mat { _p: [u8; 0] }
+#[repr(C)] pub struct srb_stream { _p: [u8; 0] }
+
+pub const SRB_ROW: i32 = 0;      // Direction::Row    (src/shared/mod.rs:39-42)
+pub const SRB_COLUMN: i32 = 1;   // Direction::Column
+pub const SRB_CSR: i32 = 0;
+pub const SRB_CSC: i32 = 1;
+pub const SRB_IDX64: i32 = 8;    // usize offsets / indices of nalgebra-sparse
+// srb_dtype: I8=0 I16=1 I32=2 (I64=3) U8=4 U16=5 U32=6 (U64=7) F32=8 F64=9
+
+#[link(name = "srb200")]
+extern "C" {
+    pub fn srb_last_error_message() -> *const c_char;
+    pub fn srb_ctx_create(device: i32, out: *mut *mut srb_ctx) -> i32;
+    pub fn srb_ctx_destroy(ctx: *mut srb_ctx) -> i32;
+    pub fn srb_ctx_set_value_mode(ctx: *mut srb_ctx, mode: i32) -> i32;
+    pub fn srb_comm_unique_id(id128: *mut c_void) -> i32;
+    pub fn srb_ctx_comm_init(ctx: *mut srb_ctx, id128: *const c_void, rank: i32, nranks: i32) -> i32;
+
+    pub fn srb_mat_upload(ctx: *mut srb_ctx, format: i32, nrows: u64, ncols: u64, nnz: u64,
+                          offsets: *const c_void, indices: *const c_void, idx_width: i32,
+                          values: *const c_void, dtype: i32, out: *mut *mut srb_mat) -> i32;
+    pub fn srb_mat_set_shard(m: *mut srb_mat, global_row0: u64, global_nrows: u64) -> i32;
+    pub fn srb_mat_clone(m: *mut srb_mat, out: *mut *mut srb_mat) -> i32;
+    pub fn srb_mat_subset(m: *mut srb_mat, keep_rows: *const u8, keep_cols: *const u8, out: *mut *mut srb_mat) -> i32;
+    pub fn srb_mat_free(m: *mut srb_mat) -> i32;
+    pub fn srb_mat_download(m: *mut srb_mat, offsets: *mut u64, indices: *mut u64,
+                            values_f64: *mut f64, values_f32: *mut f32) -> i32;
+
+    pub fn srb_number(m: *mut srb_mat, direction: i32, out: *mut u32) -> i32;
+    pub fn srb_sum(m: *mut srb_mat, direction: i32, out: *mut f64) -> i32;
+    pub fn srb_variance(m: *mut srb_mat, direction: i32, out: *mut f64) -> i32;
+    pub fn srb_std_dev(m: *mut srb_mat, direction: i32, out: *mut f64) -> i32;
+    pub fn srb_min_max(m: *mut srb_mat, direction: i32, mn: *mut f64, mx: *mut f64) -> i32;
+    pub fn srb_qc_all(m: *mut srb_mat, num_per_cell: *mut u32, num_per_gene: *mut u32,
+                      expr_per_cell: *mut f64, expr_per_gene: *mut f64,
+                      variance_per_cell: *mut f64, variance_per_gene: *mut f64,
+                      std_dev_per_cell: *mut f64, std_dev_per_gene: *mut f64) -> i32;
+
+    pub fn srb_normalize_total_inplace(m: *mut srb_mat, target_sum: f64, direction: i32) -> i32;
+    pub fn srb_log1p_inplace(m: *mut srb_mat) -> i32;
+    pub fn srb_select_hvg(m: *mut srb_mat, n_top: u64, out_idx: *mut u64, out_n: *mut u64) -> i32;
+    pub fn srb_select_var_threshold(m: *mut srb_mat, t: f64, out_idx: *mut u64, out_n: *mut u64) -> i32;
+    pub fn srb_densify_selected(m: *mut srb_mat, col_sel: *const u64, n_sel: u64, out: *mut f64) -> i32;
+    pub fn srb_pca(m: *mut srb_mat, col_sel: *const u64, n_sel: u64, k: u64, center: i32, scale: i32,
+                   gram_mode: i32, scores: *mut f64, components: *mut f64, evr: *mut f64) -> i32;
+
+    pub fn srb_stream_begin(ctx: *mut srb_ctx, format: i32, nrows_total: u64, ncols_total: u64,
+                            out: *mut *mut srb_stream) -> i32;
+    pub fn srb_stream_push(s: *mut srb_stream, nmajor_chunk: u64, nnz: u64, offsets: *const c_void,
+                           indices: *const c_void, idx_width: i32, values: *const c_void, dtype: i32) -> i32;
+    pub fn srb_stream_number(s: *mut srb_stream, direction: i32, out: *mut u32) -> i32;
+    pub fn srb_stream_sum(s: *mut srb_stream, direction: i32, out: *mut f64) -> i32;
+    pub fn srb_stream_set_retain(s: *mut srb_stream, nnz_hint: u64, keep_statistics: i32) -> i32;
+    pub fn srb_stream_finish_matrix(s: *mut srb_stream, out: *mut *mut srb_mat) -> i32;
+    pub fn srb_stream_free(s: *mut srb_stream) -> i32;
+}
+
+fn check(rc: i32) -> anyhow::Result<()> {
+    if rc == 0 { return Ok(()); }
+    let msg = unsafe { std::ffi::CStr::from_ptr(srb_last_error_message()) }.to_string_lossy().into_owned();
+    anyhow::bail!("srb200 error {rc}: {msg}")      // the crate's convention is anyhow::Result everywhere
+}

@@ -20,6 +20,7 @@
 // indices are sorted within a row; split points are found once per structure by binary search).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -143,7 +144,7 @@ struct FusedParams {
 // ---------------------------------------------------------------------------------------------------
 // (A) fused exact kernel
 // ---------------------------------------------------------------------------------------------------
-template <typename VTI, typename VTO, bool WRITE>
+template <typename VTI, typename VTO, bool WRITE, bool PIPE>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const FusedParams p) {
     extern __shared__ uint32_t bins[];
     const uint32_t W = p.W;
@@ -185,40 +186,70 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
         const VTI *vp = vin + a;
         VTO *op = vout + a;
         const int len = (int)(b - a);
-        for (int k0 = lane; k0 < len; k0 += 32 * kBatch) {
-            uint32_t cc[kBatch];
-            VTI vv[kBatch];
+        auto consume = [&](uint32_t c, VTI v, int k) {
+            const double sc = (has_scale && !p.scale_major) ? p.scale[c] : sc_row;
+            const VTO x = Xform<VTO>::apply(v, sc, has_scale, lg);
+            if (WRITE) op[k] = x;
+            uint32_t q;
+            if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
+            else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
+            const uint32_t g = c - col_lo;
+            const uint32_t o1 = atomicAdd(&s_sum[g], q);
+            const unsigned long long q2 = (unsigned long long)q * q;
+            const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
+            const uint32_t o2 = atomicAdd(&s_sqlo[g], l);
+            uint32_t c1, add3, c3, t0;
+            // carries through add.cc / addc instead of compare + select
+            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c1) : "r"(o1), "r"(q));
+            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t0), "=r"(add3) : "r"(o2), "r"(l), "r"(h));
+            const uint32_t o3 = atomicAdd(&s_sqmid[g], add3);
+            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c3) : "r"(o3), "r"(add3));
+            atomicAdd(&s_pack[g], (1u << 18) + c1 * 64u + c3);
+        };
+        if (!PIPE) {
+            for (int k0 = lane; k0 < len; k0 += 32 * kBatch) {
+                uint32_t cc[kBatch];
+                VTI vv[kBatch];
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int k = k0 + 32 * u;
-                const bool in = k < len;
-                cc[u] = in ? ip[k] : 0u;
-                vv[u] = in ? vp[k] : (VTI)0;
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int k = k0 + 32 * u;
-                if (k < len) {
-                    const uint32_t c = cc[u];
-                    const double sc = (has_scale && !p.scale_major) ? p.scale[c] : sc_row;
-                    const VTO x = Xform<VTO>::apply(vv[u], sc, has_scale, lg);
-                    if (WRITE) op[k] = x;
-                    uint32_t q;
-                    if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
-                    else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
-                    const uint32_t g = c - col_lo;
-                    const uint32_t o1 = atomicAdd(&s_sum[g], q);
-                    const unsigned long long q2 = (unsigned long long)q * q;
-                    const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
-                    const uint32_t o2 = atomicAdd(&s_sqlo[g], l);
-                    uint32_t c1, add3, c3, t0;
-                    // carries through add.cc / addc instead of compare + select
-                    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c1) : "r"(o1), "r"(q));
-                    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t0), "=r"(add3) : "r"(o2), "r"(l), "r"(h));
-                    const uint32_t o3 = atomicAdd(&s_sqmid[g], add3);
-                    asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c3) : "r"(o3), "r"(add3));
-                    atomicAdd(&s_pack[g], (1u << 18) + c1 * 64u + c3);
+                for (int u = 0; u < kBatch; ++u) {
+                    const int k = k0 + 32 * u;
+                    const bool in = k < len;
+                    cc[u] = in ? ip[k] : 0u;
+                    vv[u] = in ? vp[k] : (VTI)0;
                 }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int k = k0 + 32 * u;
+                    if (k < len) consume(cc[u], vv[u], k);
+                }
+            }
+        } else {
+            // register double buffer: the next half-batch of loads is in flight while the current one runs its atomics
+            constexpr int kHalf = kBatch / 2;
+            uint32_t cc[kHalf], cn[kHalf];
+            VTI vv[kHalf], vn[kHalf];
+            int k0 = lane;
+#pragma unroll
+            for (int u = 0; u < kHalf; ++u) {
+                const int k = k0 + 32 * u;
+                cc[u] = k < len ? ip[k] : 0u;
+                vv[u] = k < len ? vp[k] : (VTI)0;
+            }
+            for (; k0 < len; k0 += 32 * kHalf) {
+                const int kn = k0 + 32 * kHalf;
+#pragma unroll
+                for (int u = 0; u < kHalf; ++u) {
+                    const int k = kn + 32 * u;
+                    cn[u] = k < len ? ip[k] : 0u;
+                    vn[u] = k < len ? vp[k] : (VTI)0;
+                }
+#pragma unroll
+                for (int u = 0; u < kHalf; ++u) {
+                    const int k = k0 + 32 * u;
+                    if (k < len) consume(cc[u], vv[u], k);
+                }
+#pragma unroll
+                for (int u = 0; u < kHalf; ++u) cc[u] = cn[u], vv[u] = vn[u];
             }
         }
     }
@@ -453,13 +484,21 @@ static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, i
 template <typename VTI, typename VTO>
 static void launch_fused(srb_mat *m, const FusedParams &p, bool write, unsigned grid, size_t smem) {
     cudaStream_t s = m->ctx->stream;
-    if (write) {
-        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, true>), grid, kFusedThreads, smem, s, p);
-    } else {
-        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, false>), grid, kFusedThreads, smem, s, p);
+    static int pipe = -1;
+    if (pipe < 0) {
+        const char *e = getenv("SRB_FUSED_PIPE");
+        pipe = (e && e[0] == '1') ? 1 : 0;
     }
+#define SRB_FUSED_GO(W, P)                                                                                                          \
+    do {                                                                                                                            \
+        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, W, P>), grid, kFusedThreads, smem, s, p);                                          \
+    } while (0)
+    if (write && pipe) SRB_FUSED_GO(true, true);
+    else if (write) SRB_FUSED_GO(true, false);
+    else if (pipe) SRB_FUSED_GO(false, true);
+    else SRB_FUSED_GO(false, false);
+#undef SRB_FUSED_GO
 }
 
 // Apply the pending transforms; when want_moments, also produce the per-minor-line moments of the result.
