@@ -209,7 +209,9 @@ void scores_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n
 // convert.cu
 srb_mat *csc_to_csr(srb_mat *m);
 // eig.cu
-void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals_desc_out);  // C overwritten by eigenvectors
+// C overwritten by eigenvectors (column-major, ascending); returns the number of eigenpairs computed (d, or topk when the
+// range solver is selected): pair j (ascending) is column j / d_evals[j], so component c is column (count-1-c)
+uint32_t sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, uint32_t topk, double *d_evals);
 // comm.cu
 void allreduce_u64_sum(srb_ctx *ctx, uint64_t *d_buf, size_t n);
 void allreduce_f64_sum(srb_ctx *ctx, double *d_buf, size_t n);

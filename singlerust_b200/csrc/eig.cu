@@ -20,7 +20,7 @@ namespace srb {
 
 // C (row- or column-major: symmetric) is overwritten by the eigenvectors (column-major, ascending eigenvalues);
 // evals receives the ascending eigenvalues.
-void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals) {
+uint32_t sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, uint32_t topk, double *d_evals) {
     cudaStream_t s = ctx->stream;
     if (!ctx->solver) {
         cusolverDnHandle_t h;
@@ -36,9 +36,31 @@ void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals) {
     cudaStream_t es = ctx->eig_stream;
     SRB_CUSOLVER(cusolverDnSetStream(h, es));
     static int use_x = -1;  // SRB_EIG_X=1: the 64-bit generic API (cusolverDnXsyevd) instead of the legacy Dsyevd
+    static int use_range = -1;  // SRB_EIG_RANGE=1: cusolverDnDsyevdx on the index range of the top-k eigenvalues only
     if (use_x < 0) {
         const char *e = getenv("SRB_EIG_X");
         use_x = (e && e[0] == '1') ? 1 : 0;
+        const char *r = getenv("SRB_EIG_RANGE");
+        use_range = (r && r[0] == '1') ? 1 : 0;
+    }
+    if (use_range && topk < d) {
+        int lw = 0, meig = 0;
+        const int il = (int)(d - topk + 1), iu = (int)d;
+        SRB_CUSOLVER(cusolverDnDsyevdx_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d,
+                                                  0.0, 0.0, il, iu, &meig, d_evals, &lw));
+        Buf wk = dev_alloc(s, sizeof(double) * (size_t)std::max(lw, 1));
+        Buf inf = dev_zeros(s, sizeof(int));
+        SRB_CUDA(cudaEventRecord(ctx->eig_in, s));
+        SRB_CUDA(cudaStreamWaitEvent(es, ctx->eig_in, 0));
+        SRB_CUSOLVER(cusolverDnDsyevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER, (int)d, d_C, (int)d, 0.0, 0.0, il,
+                                       iu, &meig, d_evals, wk->as<double>(), lw, inf->as<int>()));
+        int hi = 0;
+        SRB_CUDA(cudaMemcpyAsync(&hi, inf->p, sizeof(int), cudaMemcpyDeviceToHost, es));
+        SRB_CUDA(cudaEventRecord(ctx->eig_out, es));
+        SRB_CUDA(cudaStreamWaitEvent(s, ctx->eig_out, 0));
+        SRB_CUDA(cudaStreamSynchronize(es));
+        SRB_REQUIRE(hi == 0 && meig == (int)topk, SRB_ERR_NAN, "syevdx failed (info=" + std::to_string(hi) + ", meig=" + std::to_string(meig) + ")");
+        return topk;
     }
     Buf info = dev_zeros(s, sizeof(int));
     Buf work;
@@ -75,6 +97,7 @@ void sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, double *d_evals) {
     SRB_CUDA(cudaStreamWaitEvent(s, ctx->eig_out, 0));
     SRB_CUDA(cudaStreamSynchronize(es));
     SRB_REQUIRE(hinfo == 0, SRB_ERR_NAN, "syevd did not converge / illegal value (info=" + std::to_string(hinfo) + "): NaN in the correlation matrix?");
+    return d;
 }
 
 void eig_destroy(srb_ctx *ctx) {

@@ -308,12 +308,12 @@ __global__ void trace_kernel(const double *__restrict__ C, uint64_t n_sel, doubl
 // eigenvectors come back column-major with ascending eigenvalues: column (n_sel-1-c) is component c.
 // Sign convention: the entry of largest magnitude of every component is positive (deterministic across runs).
 // comps[j][c] (row-major n_sel x k), W[p][c] = comps[p][c] (row-major dpad x kpad, zero padded), evr[c] = lambda_c / trace
-__global__ void components_kernel(const double *__restrict__ evec, const double *__restrict__ evals_asc, uint64_t n_sel,
+__global__ void components_kernel(const double *__restrict__ evec, const double *__restrict__ evals_asc, uint32_t npairs, uint64_t n_sel,
                                   uint32_t k, uint32_t kpad, const double *__restrict__ trace, double *__restrict__ comps,
                                   double *__restrict__ W, double *__restrict__ evr) {
     const uint32_t c = blockIdx.x;
     if (c >= k) return;
-    const double *v = evec + (n_sel - 1 - c) * n_sel;
+    const double *v = evec + (uint64_t)(npairs - 1 - c) * n_sel;
     __shared__ double s_val[256];
     __shared__ int s_idx[256];
     double best = -1.0;
@@ -339,7 +339,7 @@ __global__ void components_kernel(const double *__restrict__ evec, const double 
         comps[j * k + c] = x;
         W[j * kpad + c] = x;
     }
-    if (threadIdx.x == 0) evr[c] = evals_asc[n_sel - 1 - c] / trace[0];
+    if (threadIdx.x == 0) evr[c] = evals_asc[npairs - 1 - c] / trace[0];
 }
 
 // K9 (validation path): scores[r][c] = sum_p z[r][p] W[p][c] in fp64 on CUDA cores. One warp per 4 rows; lane l owns
@@ -460,8 +460,8 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
         StageTimer t(c, ST_EIG);
         SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, G->as<double>(), dpad, n_sel, d_sel, m->minor.sum->as<double>(), m->minor.sq->as<double>(), shift->as<double>(), inv_sd->as<double>(), n_cells, C->as<double>());
         SRB_LAUNCH(trace_kernel, 1, 256, 0, s, C->as<double>(), n_sel, tr->as<double>());
-        sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, evals->as<double>());
-        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), n_sel, (uint32_t)k, kpad, tr->as<double>(), comps->as<double>(), W->as<double>(), evr->as<double>());
+        const uint32_t npairs = sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, (uint32_t)k, evals->as<double>());
+        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), npairs, n_sel, (uint32_t)k, kpad, tr->as<double>(), comps->as<double>(), W->as<double>(), evr->as<double>());
     }
     SRB_TRACE("eig");
     // K9 scores
