@@ -57,6 +57,13 @@ typedef enum srb_index_width { SRB_IDX32 = 4, SRB_IDX64 = 8 } srb_index_width;
  *   FAITHFUL promote to f64 exactly like the reference does (scale/mod.rs:74-83, transform/mod.rs:48-55) */
 typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } srb_value_mode;
 
+/* how srb_mat_upload / srb_stream_push move the index array over PCIe (results are identical):
+ *   DEVICE_NARROW  copy the host integers as they are (8 bytes per entry for Rust usize) and narrow on the device
+ *   HOST_PACK      narrow on the host (thread pool, pinned staging ring) to 2 bytes per entry when the minor dimension
+ *                  is <= 65 536, else 4, overlap packing with the DMA, and stage pageable caller memory (a Rust Vec)
+ *                  through the same ring. Process default: environment SRB_UPLOAD_PACK (0 | 1). */
+typedef enum srb_upload_mode { SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1 } srb_upload_mode;
+
 typedef struct srb_ctx srb_ctx;
 typedef struct srb_mat srb_mat;
 
@@ -66,10 +73,17 @@ const char *srb_last_error_message(void);
 /* number of CUDA kernels launched by this library on the calling process since load (bench "gpu_launches") */
 uint64_t srb_kernel_launch_count(void);
 
+/* host helper of the HOST_PACK upload (no GPU involved; exposed so the packing can be tested and timed alone):
+ * dst[i] = src[i] narrowed from src_width (4 | 8) to dst_width (2 | 4) bytes on nthreads (<= 0: default) host threads;
+ * *out_of_bounds = 1 when any source value is >= bound. Returns 0, or -1 on a bad argument. */
+int32_t srb_host_pack_indices(const void *src, int32_t src_width, uint64_t n, void *dst, int32_t dst_width,
+                              uint64_t bound, int32_t nthreads, int32_t *out_of_bounds);
+
 /* ---- context ------------------------------------------------------------------------------------ */
 int32_t srb_ctx_create(int32_t device, srb_ctx **out);
 int32_t srb_ctx_destroy(srb_ctx *ctx);
 int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode /* srb_value_mode */);
+int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode /* srb_upload_mode */);
 int32_t srb_ctx_synchronize(srb_ctx *ctx);
 /* the cudaStream_t all work of this ctx is enqueued on (for CUDA-event timing by the caller) */
 void *srb_ctx_stream(srb_ctx *ctx);

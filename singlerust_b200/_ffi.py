@@ -14,6 +14,8 @@ ROW, COLUMN = 0, 1
 CSR, CSC = 0, 1
 VALUES_COMPACT, VALUES_FAITHFUL = 0, 1
 GRAM_TENSOR, GRAM_FP64 = 0, 1
+UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK = 0, 1
+UPLOAD_DEFAULT = "0"  # the library's built-in default for SRB_UPLOAD_PACK (api.cu: upload_pack_mode)
 
 DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
           np.dtype(np.uint8): 4, np.dtype(np.uint16): 5, np.dtype(np.uint32): 6, np.dtype(np.uint64): 7,
@@ -51,6 +53,8 @@ def lib() -> C.CDLL:
             "srb_ctx_create": [i32, C.POINTER(vp)],
             "srb_ctx_destroy": [vp],
             "srb_ctx_set_value_mode": [vp, i32],
+            "srb_ctx_set_upload_mode": [vp, i32],
+            "srb_host_pack_indices": [vp, i32, u64, vp, i32, u64, i32, C.POINTER(i32)],
             "srb_ctx_synchronize": [vp],
             "srb_comm_unique_id": [vp],
             "srb_ctx_comm_init": [vp, vp, i32, i32],
@@ -116,6 +120,17 @@ def version() -> str:
     return lib().srb_version().decode()
 
 
+def host_pack_indices(src: np.ndarray, dst_width: int, bound: int, nthreads: int = 0):
+    """Host-side narrowing used by the HOST_PACK upload (no GPU). Returns (packed array, any value >= bound)."""
+    assert src.dtype in (np.uint32, np.uint64, np.int32, np.int64) and src.flags["C_CONTIGUOUS"]
+    dst = np.empty(src.shape[0], dtype=np.uint16 if dst_width == 2 else np.uint32)
+    oob = C.c_int32(0)
+    rc = lib().srb_host_pack_indices(_ptr(src), src.dtype.itemsize, src.shape[0], _ptr(dst), dst_width, bound, nthreads, C.byref(oob))
+    if rc != 0:
+        raise ValueError("srb_host_pack_indices: bad argument")
+    return dst, bool(oob.value)
+
+
 def kernel_launch_count() -> int:
     return int(lib().srb_kernel_launch_count())
 
@@ -133,6 +148,9 @@ class Context:
 
     def set_value_mode(self, mode):
         check(lib().srb_ctx_set_value_mode(self._h, mode))
+
+    def set_upload_mode(self, mode):
+        check(lib().srb_ctx_set_upload_mode(self._h, mode))
 
     def synchronize(self):
         check(lib().srb_ctx_synchronize(self._h))

@@ -11,6 +11,9 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsrb200.so")
 SOURCES = ["api.cu", "major_stats.cu", "minor_moments.cu", "select.cu", "pca.cu", "gram_tc.cu", "gram_tc2.cu", "eig.cu", "comm.cu",
            "synth.cu", "stream.cu", "convert.cu", "subset.cu"]
+HOST_SOURCES = ["host_pack.cpp"]  # plain C++ (g++): host-side marshalling of the upload path, no CUDA
+CXX = os.environ.get("CXX", "/usr/bin/g++")
+CXXFLAGS = ["-O3", "-std=c++17", "-fPIC", "-pthread", "-Wall"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
@@ -35,9 +38,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if force or _stale(o, [s] + hdrs):
             jobs.append((s, o))
 
+    for src in HOST_SOURCES:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(objdir, src.replace(".cpp", ".o"))
+        if force or _stale(o, [s] + hdrs):
+            jobs.append((s, o))
+
     def compile_one(job):
         s, o = job
-        r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+        if s.endswith(".cpp"):
+            r = subprocess.run([CXX] + CXXFLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
+        else:
+            r = subprocess.run([NVCC] + FLAGS + ["-c", s, "-o", o], capture_output=True, text=True)
         return s, r
 
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
@@ -49,8 +61,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             with open(os.path.join(objdir, os.path.basename(s) + ".ptxas.log"), "w") as f:
                 f.write(r.stderr)
     objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in SOURCES]
+    objs += [os.path.join(objdir, src.replace(".cpp", ".o")) for src in HOST_SOURCES]
     if force or jobs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-lcusolver", "-lcuda", "-ldl",
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-lcusolver", "-lcuda", "-ldl", "-lpthread",
                                                       "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

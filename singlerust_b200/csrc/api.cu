@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "host_pack.h"
 
 namespace srb {
 
@@ -213,6 +214,83 @@ static void upload_indices(srb_ctx *c, const void *host, int width, uint64_t n, 
     }
 }
 
+// ---- packed upload ------------------------------------------------------------------------------------
+// The reference's col_indices are `usize` (8 bytes); at the bench size they are 12 of the 18 GB one step moves over
+// PCIe. SRB_UPLOAD_PACK=1 narrows them on the HOST (host_pack.cpp, a small thread pool) into a pinned staging ring —
+// 2 bytes per entry when nminor <= 65 536, else 4 — so only 2-4 bytes per entry cross the link; packing chunk c+1
+// overlaps the DMA of chunk c, and the value chunks are enqueued in between so the link never waits for the host.
+// Pageable caller memory (a Rust Vec) is staged through the same ring with a threaded memcpy instead of the
+// driver's single-threaded bounce buffer. The device widens to u32 and repeats the bounds check.
+static int upload_pack_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SRB_UPLOAD_PACK");
+        v = e ? (atoi(e) != 0) : 0;
+    }
+    return v;
+}
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static void ensure_upload_ring(srb_ctx *c, size_t bytes) {
+    if (c->up_ring_bytes >= bytes) return;
+    if (c->up_ring) {
+        SRB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->up_ring);
+        c->up_ring = nullptr, c->up_ring_bytes = 0;
+    }
+    SRB_CUDA(cudaHostAlloc(&c->up_ring, bytes, cudaHostAllocDefault));
+    c->up_ring_bytes = bytes;
+    for (int i = 0; i < srb_ctx::kUpSlots; ++i)
+        if (!c->up_ev[i]) SRB_CUDA(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+}
+// indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too
+static void upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
+                          uint32_t *d_flags, const void *values, size_t vsz, void *d_val) {
+    if (n == 0) return;
+    cudaStream_t s = c->stream;
+    const int pw = bound <= 65536 ? 2 : 4;
+    const bool stage_vals = values && host_is_pageable(values);
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 22);
+    const size_t idx_bytes = (chunk * pw + 255) & ~size_t(255);
+    const size_t slot_bytes = idx_bytes + (stage_vals ? ((chunk * vsz + 255) & ~size_t(255)) : 0);
+    ensure_upload_ring(c, slot_bytes * srb_ctx::kUpSlots);
+    Buf dpk;
+    if (pw == 2) dpk = dev_alloc(s, n * 2);
+    char *d_pk = pw == 2 ? dpk->as<char>() : (char *)d_idx;
+    bool oob = false;
+    uint64_t ci = 0;
+    for (uint64_t o = 0; o < n; o += chunk, ++ci) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - o);
+        const int slot = (int)(ci % srb_ctx::kUpSlots);
+        if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous DMA is done
+        char *h_idx = (char *)c->up_ring + slot_bytes * slot;
+        oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, 0);
+        SRB_CUDA(cudaMemcpyAsync(d_pk + o * pw, h_idx, len * pw, cudaMemcpyHostToDevice, s));
+        if (values) {
+            const char *src = (const char *)values + o * vsz;
+            if (stage_vals) {
+                host_copy_parallel(src, h_idx + idx_bytes, len * vsz, 0);
+                src = h_idx + idx_bytes;
+            }
+            SRB_CUDA(cudaMemcpyAsync((char *)d_val + o * vsz, src, len * vsz, cudaMemcpyHostToDevice, s));
+        }
+        SRB_CUDA(cudaEventRecord(c->up_ev[slot], s));
+        c->up_ev_used[slot] = true;
+    }
+    if (pw == 2)
+        SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, n), 256, 0, s, dpk->as<uint16_t>(), d_idx, n, bound, d_flags);
+    if (oob) {
+        SRB_CUDA(cudaStreamSynchronize(s));
+        throw Error(SRB_ERR_INDEX_OOB, "minor index out of bounds");
+    }
+}
+
 static void check_mat(const srb_mat *m) { SRB_REQUIRE(m && m->ctx && m->st, SRB_ERR_INVALID_ARG, "null matrix handle"); }
 static void check_dir(int d) { SRB_REQUIRE(d == SRB_ROW || d == SRB_COLUMN, SRB_ERR_INVALID_ARG, "direction must be 0 (Row) or 1 (Column)"); }
 
@@ -313,6 +391,9 @@ int32_t srb_ctx_destroy(srb_ctx *ctx) {
     release_cached_blocks(ctx->stream);
     comm_destroy(ctx);
     eig_destroy(ctx);
+    if (ctx->up_ring) cudaFreeHost(ctx->up_ring);
+    for (int i = 0; i < srb_ctx::kUpSlots; ++i)
+        if (ctx->up_ev[i]) cudaEventDestroy(ctx->up_ev[i]);
     for (int i = 0; i < ST_COUNT; ++i) {
         cudaEventDestroy(ctx->ev0[i]);
         cudaEventDestroy(ctx->ev1[i]);
@@ -327,6 +408,14 @@ int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode) {
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
     SRB_REQUIRE(mode == SRB_VALUES_COMPACT || mode == SRB_VALUES_FAITHFUL, SRB_ERR_INVALID_ARG, "bad value mode");
     ctx->value_mode = mode;
+    SRB_API_END
+}
+
+int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK, SRB_ERR_INVALID_ARG, "bad upload mode");
+    ctx->upload_mode = mode;
     SRB_API_END
 }
 
@@ -364,7 +453,8 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     } else {
         upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
     }
-    upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
+    const bool packed = (ctx->upload_mode >= 0 ? ctx->upload_mode : upload_pack_mode()) == SRB_UPLOAD_HOST_PACK;
+    if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
     std::unique_ptr<srb_mat> m(new srb_mat());
     m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
     m->src_dtype = dtype;
@@ -372,8 +462,15 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     const bool f32_exact = dtype == SRB_I8 || dtype == SRB_U8 || dtype == SRB_I16 || dtype == SRB_U16 || dtype == SRB_F32;
     m->vdtype = f32_exact ? SRB_F32 : SRB_F64;
     m->values = dev_alloc(s, (f32_exact ? 4 : 8) * (nnz ? nnz : 1));
-    if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
-    else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());
+    // values whose host dtype is the device storage dtype travel as they are, interleaved with the index chunks
+    const bool direct = (dtype == SRB_F32 && f32_exact) || (dtype == SRB_F64 && !f32_exact);
+    if (packed)
+        upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
+                      direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p);
+    if (!(packed && direct)) {
+        if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
+        else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());
+    }
     if (nmajor) SRB_LAUNCH(canonical_check_kernel, grid_for(ctx, nmajor * 32), 256, 0, s, st->offsets->as<int64_t>(), st->indices->as<uint32_t>(), nmajor, nnz, flags->as<uint32_t>());
     uint32_t hflags[2];
     int64_t last = 0;

@@ -106,6 +106,13 @@ struct srb_ctx {
     void *solver_params = nullptr;
     cudaStream_t eig_stream = nullptr;
     cudaEvent_t eig_in = nullptr, eig_out = nullptr;
+    // pinned staging ring of the packed upload path (api.cu: upload_packed), lazily allocated
+    static constexpr int kUpSlots = 4;
+    int upload_mode = -1;  // srb_upload_mode, -1 = the process default (SRB_UPLOAD_PACK)
+    void *up_ring = nullptr;
+    size_t up_ring_bytes = 0;
+    cudaEvent_t up_ev[kUpSlots] = {};
+    bool up_ev_used[kUpSlots] = {};
 };
 
 namespace srb {

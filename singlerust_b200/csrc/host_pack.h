@@ -1,0 +1,13 @@
+// host_pack.h — host-side packing helpers of the upload path (host_pack.cpp; plain C++, no CUDA).
+#pragma once
+#include <cstdint>
+
+namespace srb {
+// threads the upload path uses (SRB_UPLOAD_THREADS, default min(hardware threads, 16))
+int host_pack_threads();
+// dst[i] = (narrow) src[i] for i < n, src entries `src_width` (4|8) bytes, dst entries `dst_width` (2|4) bytes;
+// returns true when any source value is >= bound. nthreads <= 0: the default.
+bool host_pack_indices(const void *src, int src_width, uint64_t n, void *dst, int dst_width, uint64_t bound, int nthreads);
+// threaded memcpy (pageable host memory -> pinned staging ring)
+void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads);
+}  // namespace srb
