@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--inflight", type=int, default=1, help="batches in flight per GPU (one context + stream + host thread each): "
                     "the latency-bound eigensolver of batch i overlaps the bandwidth-bound kernels of batch i+1")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--upload-mode", default="default", choices=["default", "device_narrow", "host_pack"],
+    ap.add_argument("--upload-mode", default="default", choices=["default", "device_narrow", "host_pack", "auto"],
                     help="how the e2e leg moves the u64 index array over PCIe (srb_ctx_set_upload_mode); default = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -404,11 +404,8 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
     if src is not mat:
         src.free()
 
-    mode = args.upload_mode
-    if mode == "default":
-        mode = "host_pack" if os.environ.get("SRB_UPLOAD_PACK", _ffi.UPLOAD_DEFAULT) == "1" else "device_narrow"
-    ctx.set_upload_mode(_ffi.UPLOAD_HOST_PACK if mode == "host_pack" else _ffi.UPLOAD_DEVICE_NARROW)
-    idx_bytes_on_link = (2 if args.genes <= 65536 else 4) if mode == "host_pack" else 8
+    if args.upload_mode != "default":
+        ctx.set_upload_mode({"device_narrow": _ffi.UPLOAD_DEVICE_NARROW, "host_pack": _ffi.UPLOAD_HOST_PACK, "auto": _ffi.UPLOAD_AUTO}[args.upload_mode])
 
     def step():
         m = _ffi.DeviceMatrix.upload(ctx, _ffi.CSR, n, args.genes, off, idx, val, nnz=nnz, idx_width=8, dtype=_ffi.F32)
@@ -429,11 +426,11 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.e2e_steps
-    h2d = 8 * (n + 1) + (idx_bytes_on_link + 4) * nnz  # bytes that actually cross PCIe
+    h2d, packed = ctx.last_upload()  # bytes that actually crossed PCIe (the library's own count)
     d2h = 8 * n * k + 8 * min(args.hvg, args.genes) * (k + 1) + 8 * k
     return {"value": world * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": ms, "steps": args.e2e_steps, "cells_per_gpu": n,
-            "host_input_bytes_per_step": int(8 * (n + 1) + 12 * nnz), "upload_mode": mode,
+            "host_input_bytes_per_step": int(8 * (n + 1) + 12 * nnz), "upload_mode": "host_pack" if packed else "device_narrow",
             "host_layout": "u64 offsets + u64 indices + f32 values in pinned memory (the Rust usize layout)"}
 
 

@@ -61,8 +61,11 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *   DEVICE_NARROW  copy the host integers as they are (8 bytes per entry for Rust usize) and narrow on the device
  *   HOST_PACK      narrow on the host (thread pool, pinned staging ring) to 2 bytes per entry when the minor dimension
  *                  is <= 65 536, else 4, overlap packing with the DMA, and stage pageable caller memory (a Rust Vec)
- *                  through the same ring. Process default: environment SRB_UPLOAD_PACK (0 | 1). */
-typedef enum srb_upload_mode { SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1 } srb_upload_mode;
+ *                  through the same ring
+ *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
+ *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
+ * Process default: environment SRB_UPLOAD_PACK (0 | 1 | auto). */
+typedef enum srb_upload_mode { SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2 } srb_upload_mode;
 
 typedef struct srb_ctx srb_ctx;
 typedef struct srb_mat srb_mat;
@@ -84,6 +87,8 @@ int32_t srb_ctx_create(int32_t device, srb_ctx **out);
 int32_t srb_ctx_destroy(srb_ctx *ctx);
 int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode /* srb_value_mode */);
 int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode /* srb_upload_mode */);
+/* what the last srb_mat_upload on this ctx moved over the link: bytes, and whether the index array was host-packed */
+int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_packed);
 int32_t srb_ctx_synchronize(srb_ctx *ctx);
 /* the cudaStream_t all work of this ctx is enqueued on (for CUDA-event timing by the caller) */
 void *srb_ctx_stream(srb_ctx *ctx);

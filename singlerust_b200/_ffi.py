@@ -14,7 +14,7 @@ ROW, COLUMN = 0, 1
 CSR, CSC = 0, 1
 VALUES_COMPACT, VALUES_FAITHFUL = 0, 1
 GRAM_TENSOR, GRAM_FP64 = 0, 1
-UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK = 0, 1
+UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK, UPLOAD_AUTO = 0, 1, 2
 UPLOAD_DEFAULT = "0"  # the library's built-in default for SRB_UPLOAD_PACK (api.cu: upload_pack_mode)
 
 DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
             "srb_ctx_set_value_mode": [vp, i32],
             "srb_ctx_set_upload_mode": [vp, i32],
             "srb_host_pack_indices": [vp, i32, u64, vp, i32, u64, i32, C.POINTER(i32)],
+            "srb_ctx_last_upload": [vp, C.POINTER(u64), C.POINTER(i32)],
             "srb_ctx_synchronize": [vp],
             "srb_comm_unique_id": [vp],
             "srb_ctx_comm_init": [vp, vp, i32, i32],
@@ -151,6 +152,12 @@ class Context:
 
     def set_upload_mode(self, mode):
         check(lib().srb_ctx_set_upload_mode(self._h, mode))
+
+    def last_upload(self):
+        """(bytes the last upload moved over the link, index array was host-packed)"""
+        b, p = C.c_uint64(0), C.c_int32(0)
+        check(lib().srb_ctx_last_upload(self._h, C.byref(b), C.byref(p)))
+        return int(b.value), bool(p.value)
 
     def synchronize(self):
         check(lib().srb_ctx_synchronize(self._h))

@@ -11,6 +11,9 @@
 #include "common.cuh"
 #include "host_pack.h"
 
+// built-in default of SRB_UPLOAD_PACK (kept in step with _ffi.UPLOAD_DEFAULT)
+#define SRB_UPLOAD_DEFAULT_MODE SRB_UPLOAD_DEVICE_NARROW
+
 namespace srb {
 
 static thread_local std::string t_last_error;
@@ -225,9 +228,20 @@ static int upload_pack_mode() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SRB_UPLOAD_PACK");
-        v = e ? (atoi(e) != 0) : 0;
+        if (!e) v = SRB_UPLOAD_DEFAULT_MODE;
+        else if (!strcmp(e, "auto")) v = SRB_UPLOAD_AUTO;
+        else v = atoi(e) != 0 ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
     }
     return v;
+}
+// host threads one context may use for packing: the ranks of a node share its cores
+static int upload_threads(const srb_ctx *c) { return std::max(1, host_pack_threads() / std::max(1, c->nranks)); }
+// AUTO: packing pays when the host narrows faster than the link moves the unpacked array (12 B per entry at ~55 GB/s =
+// 4.6 G entries/s; one host thread packs ~0.9 G entries/s), i.e. with >= 6 threads, and only for arrays worth a ring
+static bool use_packed_upload(const srb_ctx *c, uint64_t nnz) {
+    const int mode = c->upload_mode >= 0 ? c->upload_mode : upload_pack_mode();
+    if (mode == SRB_UPLOAD_AUTO) return nnz >= (1ull << 20) && upload_threads(c) >= 6;
+    return mode == SRB_UPLOAD_HOST_PACK;
 }
 static bool host_is_pageable(const void *p) {
     cudaPointerAttributes a;
@@ -255,6 +269,7 @@ static void upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n
     if (n == 0) return;
     cudaStream_t s = c->stream;
     const int pw = bound <= 65536 ? 2 : 4;
+    const int nthreads = upload_threads(c);
     const bool stage_vals = values && host_is_pageable(values);
     const uint64_t chunk = std::min<uint64_t>(n, 1ull << 22);
     const size_t idx_bytes = (chunk * pw + 255) & ~size_t(255);
@@ -270,12 +285,12 @@ static void upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n
         const int slot = (int)(ci % srb_ctx::kUpSlots);
         if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous DMA is done
         char *h_idx = (char *)c->up_ring + slot_bytes * slot;
-        oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, 0);
+        oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
         SRB_CUDA(cudaMemcpyAsync(d_pk + o * pw, h_idx, len * pw, cudaMemcpyHostToDevice, s));
         if (values) {
             const char *src = (const char *)values + o * vsz;
             if (stage_vals) {
-                host_copy_parallel(src, h_idx + idx_bytes, len * vsz, 0);
+                host_copy_parallel(src, h_idx + idx_bytes, len * vsz, nthreads);
                 src = h_idx + idx_bytes;
             }
             SRB_CUDA(cudaMemcpyAsync((char *)d_val + o * vsz, src, len * vsz, cudaMemcpyHostToDevice, s));
@@ -414,8 +429,16 @@ int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode) {
 int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
     SRB_API_BEGIN
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
-    SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK, SRB_ERR_INVALID_ARG, "bad upload mode");
+    SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO, SRB_ERR_INVALID_ARG, "bad upload mode");
     ctx->upload_mode = mode;
+    SRB_API_END
+}
+
+int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_packed) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    if (h2d_bytes) *h2d_bytes = ctx->last_upload_h2d;
+    if (host_packed) *host_packed = ctx->last_upload_packed;
     SRB_API_END
 }
 
@@ -453,7 +476,7 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     } else {
         upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
     }
-    const bool packed = (ctx->upload_mode >= 0 ? ctx->upload_mode : upload_pack_mode()) == SRB_UPLOAD_HOST_PACK;
+    const bool packed = use_packed_upload(ctx, nnz);
     if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
     std::unique_ptr<srb_mat> m(new srb_mat());
     m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
@@ -470,6 +493,12 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     if (!(packed && direct)) {
         if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
         else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());
+    }
+    {
+        static const size_t esz[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+        const uint64_t iw = packed ? (nminor <= 65536 ? 2 : 4) : (uint64_t)idx_width;
+        ctx->last_upload_h2d = (uint64_t)idx_width * (nmajor + 1) + iw * nnz + esz[dtype] * nnz;
+        ctx->last_upload_packed = packed ? 1 : 0;
     }
     if (nmajor) SRB_LAUNCH(canonical_check_kernel, grid_for(ctx, nmajor * 32), 256, 0, s, st->offsets->as<int64_t>(), st->indices->as<uint32_t>(), nmajor, nnz, flags->as<uint32_t>());
     uint32_t hflags[2];

@@ -109,6 +109,8 @@ struct srb_ctx {
     // pinned staging ring of the packed upload path (api.cu: upload_packed), lazily allocated
     static constexpr int kUpSlots = 4;
     int upload_mode = -1;  // srb_upload_mode, -1 = the process default (SRB_UPLOAD_PACK)
+    uint64_t last_upload_h2d = 0;  // bytes the last srb_mat_upload moved over the link
+    int last_upload_packed = 0;
     void *up_ring = nullptr;
     size_t up_ring_bytes = 0;
     cudaEvent_t up_ev[kUpSlots] = {};
