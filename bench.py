@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--inflight", type=int, default=1, help="batches in flight per GPU (one context + stream + host thread each): "
                     "the latency-bound eigensolver of batch i overlaps the bandwidth-bound kernels of batch i+1")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-inflight", type=int, default=2, help="e2e steps in flight on one GPU (one context + stream + host "
+                    "thread each): the upload of step i+1 overlaps the kernels and the score download of step i. N = 1 only")
     ap.add_argument("--upload-mode", default="default", choices=["default", "device_narrow", "host_pack", "auto"],
                     help="how the e2e leg moves the u64 index array over PCIe (srb_ctx_set_upload_mode); default = library default")
     ap.add_argument("--no-e2e", action="store_true")
@@ -404,32 +406,73 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
     if src is not mat:
         src.free()
 
-    if args.upload_mode != "default":
-        ctx.set_upload_mode({"device_narrow": _ffi.UPLOAD_DEVICE_NARROW, "host_pack": _ffi.UPLOAD_HOST_PACK, "auto": _ffi.UPLOAD_AUTO}[args.upload_mode])
+    modes = {"device_narrow": _ffi.UPLOAD_DEVICE_NARROW, "host_pack": _ffi.UPLOAD_HOST_PACK, "auto": _ffi.UPLOAD_AUTO}
+    # lanes: independent contexts on this GPU; with more than one rank every lane would need its own communicator and a
+    # rank-consistent collective order, so pipelining is a single-GPU feature
+    L = max(1, args.e2e_inflight) if world == 1 else 1
+    lanes = [ctx] + [_ffi.Context(ctx.device) for _ in range(L - 1)]
+    for c in lanes:
+        if args.upload_mode != "default":
+            c.set_upload_mode(modes[args.upload_mode])
+    lane_scores = [scores] + [torch.empty((n, k), dtype=torch.float64).pin_memory() for _ in range(L - 1)]
 
-    def step():
-        m = _ffi.DeviceMatrix.upload(ctx, _ffi.CSR, n, args.genes, off, idx, val, nnz=nnz, idx_width=8, dtype=_ffi.F32)
+    def step(lane=0):
+        c = lanes[lane]
+        m = _ffi.DeviceMatrix.upload(c, _ffi.CSR, n, args.genes, off, idx, val, nnz=nnz, idx_width=8, dtype=_ffi.F32)
         m.set_shard(rank * n, world * n)
-        m.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, scores_out=scores)
+        m.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, scores_out=lane_scores[lane])
         m.free()
 
-    step()  # warm-up (allocations, first touch of the pinned pages)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.e2e_steps):
-        step()
-    e1.record(stream)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.e2e_steps
+    def timed(n_steps, n_lanes):
+        """n_steps e2e steps round-robin over n_lanes host threads; device time from the first start event to the last
+        end event, max over ranks."""
+        use = list(range(n_lanes))
+        streams = [torch.cuda.ExternalStream(lanes[l].stream, device=dev) for l in use]
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in use]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in use]
+
+        def worker(l):
+            for _ in range(l, n_steps, n_lanes):
+                step(l)
+
+        barrier()
+        for l in use:
+            lanes[l].synchronize()
+        for e, st_ in zip(e0, streams):
+            e.record(st_)
+        if n_lanes == 1:
+            worker(0)
+        else:
+            ts = [threading.Thread(target=worker, args=(l,)) for l in use]
+            for t_ in ts:
+                t_.start()
+            for t_ in ts:
+                t_.join()
+        for e, st_ in zip(e1, streams):
+            e.record(st_)
+        for l in use:
+            lanes[l].synchronize()
+        barrier()
+        t = torch.tensor([max(a.elapsed_time(b) for a in e0 for b in e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n_steps
+
+    for l in range(L):
+        step(l)  # warm-up (allocations, staging ring, first touch of the pinned pages)
+    ms_seq = timed(args.e2e_steps, 1)
+    ms = ms_seq
+    if L > 1:
+        ms_pipe = timed(max(args.e2e_steps, 2) * L, L)
+        ms = min(ms_seq, ms_pipe)
     h2d, packed = ctx.last_upload()  # bytes that actually crossed PCIe (the library's own count)
+    for c in lanes[1:]:
+        c.close()
     d2h = 8 * n * k + 8 * min(args.hvg, args.genes) * (k + 1) + 8 * k
     return {"value": world * n / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ms_per_step": ms, "steps": args.e2e_steps, "cells_per_gpu": n,
+            "steps_in_flight": (L if (L > 1 and ms == ms_pipe) else 1), "ms_per_step_sequential": ms_seq,
+            "ms_per_step_pipelined": (ms_pipe if L > 1 else None),
             "host_input_bytes_per_step": int(8 * (n + 1) + 12 * nnz), "upload_mode": "host_pack" if packed else "device_narrow",
             "host_layout": "u64 offsets + u64 indices + f32 values in pinned memory (the Rust usize layout)"}
 

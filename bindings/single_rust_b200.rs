@@ -16,10 +16,19 @@ pub const SRB_IDX64: i32 = 8;    // usize offsets / indices of nalgebra-sparse
 
 #[link(name = "srb200")]
 extern "C" {
+    pub fn srb_version() -> *const c_char;
     pub fn srb_last_error_message() -> *const c_char;
+    pub fn srb_kernel_launch_count() -> u64;
+    pub fn srb_host_pack_indices(src: *const c_void, src_width: i32, n: u64, dst: *mut c_void, dst_width: i32,
+                                 bound: u64, nthreads: i32, out_of_bounds: *mut i32) -> i32;
     pub fn srb_ctx_create(device: i32, out: *mut *mut srb_ctx) -> i32;
     pub fn srb_ctx_destroy(ctx: *mut srb_ctx) -> i32;
     pub fn srb_ctx_set_value_mode(ctx: *mut srb_ctx, mode: i32) -> i32;
+    pub fn srb_ctx_set_upload_mode(ctx: *mut srb_ctx, mode: i32) -> i32;   // 0 device-narrow, 1 host-pack, 2 auto
+    pub fn srb_ctx_last_upload(ctx: *mut srb_ctx, h2d_bytes: *mut u64, host_packed: *mut i32) -> i32;
+    pub fn srb_ctx_synchronize(ctx: *mut srb_ctx) -> i32;
+    pub fn srb_ctx_stream(ctx: *mut srb_ctx) -> *mut c_void;
+    pub fn srb_last_stage_ms(ctx: *mut srb_ctx, out_ms: *mut f32, n: i32) -> i32;
     pub fn srb_comm_unique_id(id128: *mut c_void) -> i32;
     pub fn srb_ctx_comm_init(ctx: *mut srb_ctx, id128: *const c_void, rank: i32, nranks: i32) -> i32;
 
@@ -30,6 +39,10 @@ extern "C" {
     pub fn srb_mat_clone(m: *mut srb_mat, out: *mut *mut srb_mat) -> i32;
     pub fn srb_mat_subset(m: *mut srb_mat, keep_rows: *const u8, keep_cols: *const u8, out: *mut *mut srb_mat) -> i32;
     pub fn srb_mat_free(m: *mut srb_mat) -> i32;
+    pub fn srb_mat_info(m: *mut srb_mat, nrows: *mut u64, ncols: *mut u64, nnz: *mut u64, format: *mut i32,
+                        value_dtype: *mut i32) -> i32;
+    pub fn srb_synth_csr(ctx: *mut srb_ctx, seed: u32, skew: i32, row0: u64, nrows: u64, ncols: u32,
+                         thr: *const u32, amp: *const u32, out: *mut *mut srb_mat) -> i32;
     pub fn srb_mat_download(m: *mut srb_mat, offsets: *mut u64, indices: *mut u64,
                             values_f64: *mut f64, values_f32: *mut f32) -> i32;
 
@@ -51,12 +64,17 @@ extern "C" {
     pub fn srb_pca(m: *mut srb_mat, col_sel: *const u64, n_sel: u64, k: u64, center: i32, scale: i32,
                    gram_mode: i32, scores: *mut f64, components: *mut f64, evr: *mut f64) -> i32;
 
+    pub fn srb_pipeline_normalize_hvg_pca(m: *mut srb_mat, target_sum: f64, n_top: u64, k: u64, center: i32, scale: i32,
+                                          gram_mode: i32, hvg_out: *mut u64, scores: *mut f64, components: *mut f64,
+                                          evr: *mut f64) -> i32;
+
     pub fn srb_stream_begin(ctx: *mut srb_ctx, format: i32, nrows_total: u64, ncols_total: u64,
                             out: *mut *mut srb_stream) -> i32;
     pub fn srb_stream_push(s: *mut srb_stream, nmajor_chunk: u64, nnz: u64, offsets: *const c_void,
                            indices: *const c_void, idx_width: i32, values: *const c_void, dtype: i32) -> i32;
     pub fn srb_stream_number(s: *mut srb_stream, direction: i32, out: *mut u32) -> i32;
     pub fn srb_stream_sum(s: *mut srb_stream, direction: i32, out: *mut f64) -> i32;
+    pub fn srb_stream_variance(s: *mut srb_stream, direction: i32, out: *mut f64) -> i32;
     pub fn srb_stream_set_retain(s: *mut srb_stream, nnz_hint: u64, keep_statistics: i32) -> i32;
     pub fn srb_stream_finish_matrix(s: *mut srb_stream, out: *mut *mut srb_mat) -> i32;
     pub fn srb_stream_free(s: *mut srb_stream) -> i32;

@@ -64,7 +64,7 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *                  through the same ring
  *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
  *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
- * Process default: environment SRB_UPLOAD_PACK (0 | 1 | auto). */
+ * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto) overrides it. */
 typedef enum srb_upload_mode { SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2 } srb_upload_mode;
 
 typedef struct srb_ctx srb_ctx;

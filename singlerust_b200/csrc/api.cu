@@ -12,7 +12,7 @@
 #include "host_pack.h"
 
 // built-in default of SRB_UPLOAD_PACK (kept in step with _ffi.UPLOAD_DEFAULT)
-#define SRB_UPLOAD_DEFAULT_MODE SRB_UPLOAD_DEVICE_NARROW
+#define SRB_UPLOAD_DEFAULT_MODE SRB_UPLOAD_AUTO
 
 namespace srb {
 

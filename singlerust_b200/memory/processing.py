@@ -12,14 +12,27 @@ from ..shared import Direction, FeatureSelection
 F64_MIN, F64_MAX = -np.finfo(np.float64).max, np.finfo(np.float64).max
 
 
+def linear_quantile(values, q: float) -> float:
+    """ndarray_stats::interpolate::Linear on the sorted values: index q (n - 1); lower + (higher - lower) * frac.
+    (NumPy's 'linear' method evaluates the same point with a differently rounded lerp for frac >= 0.5.)"""
+    v = np.sort(np.asarray(values, dtype=np.float64))
+    if v.size == 0:
+        raise ValueError("Error calculating percentile: empty input")
+    if not 0.0 <= q <= 1.0:
+        raise ValueError("Error calculating percentile: q outside [0, 1]")
+    pos = q * (v.size - 1)
+    lo, hi = int(np.floor(pos)), int(np.ceil(pos))
+    return float(v[lo] + (v[hi] - v[lo]) * (pos - lo))
+
+
 def calculate_percentiles(values, lower_lim, upper_lim):
-    """processing/mod.rs:148-174: ndarray-stats quantile with Linear interpolation (= NumPy's default 'linear');
-    f64::MIN / f64::MAX when the limit is not Relative."""
+    """processing/mod.rs:148-174: ndarray-stats quantile with Linear interpolation; f64::MIN / f64::MAX when the limit
+    is not Relative."""
     v = np.asarray(values, dtype=np.float64)
     if np.isnan(v).any():
         raise ValueError("NaN in the per-line sums (noisy_float n64 panics in the reference)")
-    lo = float(np.quantile(v, lower_lim.value)) if lower_lim.is_relative() else F64_MIN
-    hi = float(np.quantile(v, upper_lim.value)) if upper_lim.is_relative() else F64_MAX
+    lo = linear_quantile(v, lower_lim.value) if lower_lim.is_relative() else F64_MIN
+    hi = linear_quantile(v, upper_lim.value) if upper_lim.is_relative() else F64_MAX
     return lo, hi
 
 

@@ -24,6 +24,21 @@ def test_abi_library_exports_every_declared_symbol():
     _ffi.lib()  # prototypes resolve
 
 
+def test_bindings_declare_every_header_symbol():
+    """The Rust extern block (bindings/single_rust_b200.rs, mirrored in INTEGRATION.md) and the ctypes table bind the
+    same symbol set as include/srb200.h — none missing, none invented."""
+    from singlerust_b200 import _ffi
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "srb200.h")).read(), flags=re.S)
+    names = set(re.findall(r"\b(srb_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "bindings", "single_rust_b200.rs")).read()
+    rs_names = set(re.findall(r"pub fn (srb_[a-z0-9_]+)\s*\(", rs))
+    assert rs_names == names, (sorted(names - rs_names), sorted(rs_names - names))
+    lib = _ffi.lib()
+    untyped = [n for n in names if getattr(lib, n).argtypes is None and n not in
+               ("srb_version", "srb_last_error_message", "srb_kernel_launch_count")]
+    assert not untyped, untyped
+
+
 def test_no_gpu_fails_loudly():
     """No CPU fallback: without a device the product path raises (this container has no GPU)."""
     import torch
