@@ -19,6 +19,8 @@ extern "C" {
     pub fn srb_version() -> *const c_char;
     pub fn srb_last_error_message() -> *const c_char;
     pub fn srb_kernel_launch_count() -> u64;
+    pub fn srb_host_pack_values_f32(src: *const f32, n: u64, dst: *mut c_void, dst_width: i32, nthreads: i32,
+                                    lossless: *mut i32) -> i32;
     pub fn srb_host_pack_indices(src: *const c_void, src_width: i32, n: u64, dst: *mut c_void, dst_width: i32,
                                  bound: u64, nthreads: i32, out_of_bounds: *mut i32) -> i32;
     pub fn srb_ctx_create(device: i32, out: *mut *mut srb_ctx) -> i32;

@@ -61,7 +61,8 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *   DEVICE_NARROW  copy the host integers as they are (8 bytes per entry for Rust usize) and narrow on the device
  *   HOST_PACK      narrow on the host (thread pool, pinned staging ring) to 2 bytes per entry when the minor dimension
  *                  is <= 65 536, else 4, overlap packing with the DMA, and stage pageable caller memory (a Rust Vec)
- *                  through the same ring
+ *                  through the same ring; f32 values travel as u8 / u16 for every chunk in which that is lossless
+ *                  (raw counts), bit-identical f32 on the device (SRB_UPLOAD_PACK_VALUES=0 disables)
  *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
  *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
  * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto) overrides it. */
@@ -81,6 +82,11 @@ uint64_t srb_kernel_launch_count(void);
  * *out_of_bounds = 1 when any source value is >= bound. Returns 0, or -1 on a bad argument. */
 int32_t srb_host_pack_indices(const void *src, int32_t src_width, uint64_t n, void *dst, int32_t dst_width,
                               uint64_t bound, int32_t nthreads, int32_t *out_of_bounds);
+
+/* the value twin: f32 counts -> dst_width (1 | 2) byte integers; *lossless = 1 iff every value is an integer in
+ * [0, 2^(8 dst_width)) whose f32 bit pattern the device can rebuild exactly (else dst is unspecified) */
+int32_t srb_host_pack_values_f32(const float *src, uint64_t n, void *dst, int32_t dst_width, int32_t nthreads,
+                                 int32_t *lossless);
 
 /* ---- context ------------------------------------------------------------------------------------ */
 int32_t srb_ctx_create(int32_t device, srb_ctx **out);

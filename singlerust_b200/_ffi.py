@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
             "srb_ctx_set_upload_mode": [vp, i32],
             "srb_host_pack_indices": [vp, i32, u64, vp, i32, u64, i32, C.POINTER(i32)],
             "srb_ctx_last_upload": [vp, C.POINTER(u64), C.POINTER(i32)],
+            "srb_host_pack_values_f32": [vp, u64, vp, i32, i32, C.POINTER(i32)],
             "srb_ctx_synchronize": [vp],
             "srb_comm_unique_id": [vp],
             "srb_ctx_comm_init": [vp, vp, i32, i32],
@@ -129,6 +130,16 @@ def host_pack_indices(src: np.ndarray, dst_width: int, bound: int, nthreads: int
     if rc != 0:
         raise ValueError("srb_host_pack_indices: bad argument")
     return dst, bool(oob.value)
+
+
+def host_pack_values_f32(src: np.ndarray, dst_width: int, nthreads: int = 0):
+    """Host-side lossless narrowing of f32 counts (no GPU). Returns (packed array, lossless)."""
+    assert src.dtype == np.float32 and src.flags["C_CONTIGUOUS"]
+    dst = np.empty(src.shape[0], dtype=np.uint8 if dst_width == 1 else np.uint16)
+    ok = C.c_int32(0)
+    if lib().srb_host_pack_values_f32(_ptr(src), src.shape[0], _ptr(dst), dst_width, nthreads, C.byref(ok)) != 0:
+        raise ValueError("srb_host_pack_values_f32: bad argument")
+    return dst, bool(ok.value)
 
 
 def kernel_launch_count() -> int:

@@ -263,47 +263,98 @@ static void ensure_upload_ring(srb_ctx *c, size_t bytes) {
     for (int i = 0; i < srb_ctx::kUpSlots; ++i)
         if (!c->up_ev[i]) SRB_CUDA(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
 }
-// indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too
-static void upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
-                          uint32_t *d_flags, const void *values, size_t vsz, void *d_val) {
-    if (n == 0) return;
+// f32 chunk values that travelled as u8 / u16 (widths[chunk] = 1 | 2; 0 = the chunk was copied raw): rebuild the f32 array.
+// Packed chunk c sits at byte offset 2 * c * chunk of `pk`.
+__global__ void unpack_values_kernel(const uint8_t *__restrict__ pk, float *__restrict__ out, uint64_t n, int chunk_shift,
+                                     const uint8_t *__restrict__ widths) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = i >> chunk_shift, base = c << chunk_shift;  // a single chunk (n < 2^shift) has c = 0
+        const uint8_t w = widths[c];
+        if (w == 1) out[i] = (float)pk[2 * base + (i - base)];
+        else if (w == 2) out[i] = (float)reinterpret_cast<const uint16_t *>(pk)[i];
+    }
+}
+static bool upload_pack_values() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SRB_UPLOAD_PACK_VALUES");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v == 1;
+}
+// indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too.
+// Returns the bytes that crossed the link.
+static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
+                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val) {
+    if (n == 0) return 0;
     cudaStream_t s = c->stream;
     const int pw = bound <= 65536 ? 2 : 4;
     const int nthreads = upload_threads(c);
     const bool stage_vals = values && host_is_pageable(values);
-    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 22);
+    const bool pack_vals = values && vsz == 4 && upload_pack_values();  // f32 counts -> u8 / u16 where lossless
+    constexpr int kChunkShift = 22;
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << kChunkShift);
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
     const size_t idx_bytes = (chunk * pw + 255) & ~size_t(255);
-    const size_t slot_bytes = idx_bytes + (stage_vals ? ((chunk * vsz + 255) & ~size_t(255)) : 0);
+    const size_t val_bytes = stage_vals ? chunk * vsz : (pack_vals ? chunk * 2 : 0);
+    const size_t slot_bytes = idx_bytes + ((val_bytes + 255) & ~size_t(255));
     ensure_upload_ring(c, slot_bytes * srb_ctx::kUpSlots);
-    Buf dpk;
+    Buf dpk, dvpk;
     if (pw == 2) dpk = dev_alloc(s, n * 2);
+    if (pack_vals) dvpk = dev_alloc(s, nchunks * chunk * 2);
     char *d_pk = pw == 2 ? dpk->as<char>() : (char *)d_idx;
-    bool oob = false;
-    uint64_t ci = 0;
+    std::vector<uint8_t> widths(nchunks, 0);
+    int vstate = pack_vals ? 1 : 0;  // 1: try u8, 2: try u16, 0: raw (sticky: a chunk that refuses widens all later ones)
+    bool oob = false, any_packed = false;
+    uint64_t ci = 0, link = 0;
     for (uint64_t o = 0; o < n; o += chunk, ++ci) {
         const uint64_t len = std::min<uint64_t>(chunk, n - o);
         const int slot = (int)(ci % srb_ctx::kUpSlots);
         if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous DMA is done
-        char *h_idx = (char *)c->up_ring + slot_bytes * slot;
+        char *h_idx = (char *)c->up_ring + slot_bytes * slot, *h_val = h_idx + idx_bytes;
         oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
         SRB_CUDA(cudaMemcpyAsync(d_pk + o * pw, h_idx, len * pw, cudaMemcpyHostToDevice, s));
+        link += len * pw;
         if (values) {
             const char *src = (const char *)values + o * vsz;
-            if (stage_vals) {
-                host_copy_parallel(src, h_idx + idx_bytes, len * vsz, nthreads);
-                src = h_idx + idx_bytes;
+            int w = 0;
+            while (vstate) {
+                if (host_pack_values_f32((const float *)src, len, h_val, vstate, nthreads)) {
+                    w = vstate;
+                    break;
+                }
+                vstate = vstate == 1 ? 2 : 0;
             }
-            SRB_CUDA(cudaMemcpyAsync((char *)d_val + o * vsz, src, len * vsz, cudaMemcpyHostToDevice, s));
+            widths[ci] = (uint8_t)w;
+            if (w) {
+                SRB_CUDA(cudaMemcpyAsync(dvpk->as<char>() + 2 * o, h_val, len * w, cudaMemcpyHostToDevice, s));
+                link += len * w;
+                any_packed = true;
+            } else {
+                if (stage_vals) {
+                    host_copy_parallel(src, h_val, len * vsz, nthreads);
+                    src = h_val;
+                }
+                SRB_CUDA(cudaMemcpyAsync((char *)d_val + o * vsz, src, len * vsz, cudaMemcpyHostToDevice, s));
+                link += len * vsz;
+            }
         }
         SRB_CUDA(cudaEventRecord(c->up_ev[slot], s));
         c->up_ev_used[slot] = true;
     }
     if (pw == 2)
         SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, n), 256, 0, s, dpk->as<uint16_t>(), d_idx, n, bound, d_flags);
+    if (any_packed) {
+        Buf dw = dev_alloc(s, nchunks);
+        SRB_CUDA(cudaMemcpyAsync(dw->p, widths.data(), nchunks, cudaMemcpyHostToDevice, s));
+        SRB_LAUNCH(unpack_values_kernel, grid_for(c, n), 256, 0, s, dvpk->as<uint8_t>(), (float *)d_val, n, kChunkShift, dw->as<uint8_t>());
+        SRB_CUDA(cudaStreamSynchronize(s));  // `widths` (pageable) and the staging ring are done with
+    }
     if (oob) {
         SRB_CUDA(cudaStreamSynchronize(s));
         throw Error(SRB_ERR_INDEX_OOB, "minor index out of bounds");
     }
+    return link;
 }
 
 static void check_mat(const srb_mat *m) { SRB_REQUIRE(m && m->ctx && m->st, SRB_ERR_INVALID_ARG, "null matrix handle"); }
@@ -487,17 +538,18 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     m->values = dev_alloc(s, (f32_exact ? 4 : 8) * (nnz ? nnz : 1));
     // values whose host dtype is the device storage dtype travel as they are, interleaved with the index chunks
     const bool direct = (dtype == SRB_F32 && f32_exact) || (dtype == SRB_F64 && !f32_exact);
+    uint64_t link_bytes = 0;
     if (packed)
-        upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
-                      direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p);
+        link_bytes = upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
+                                   direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p);
     if (!(packed && direct)) {
         if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
         else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());
     }
     {
         static const size_t esz[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
-        const uint64_t iw = packed ? (nminor <= 65536 ? 2 : 4) : (uint64_t)idx_width;
-        ctx->last_upload_h2d = (uint64_t)idx_width * (nmajor + 1) + iw * nnz + esz[dtype] * nnz;
+        ctx->last_upload_h2d = (uint64_t)idx_width * (nmajor + 1) +
+                               (packed ? link_bytes + (direct ? 0 : esz[dtype] * nnz) : ((uint64_t)idx_width + esz[dtype]) * nnz);
         ctx->last_upload_packed = packed ? 1 : 0;
     }
     if (nmajor) SRB_LAUNCH(canonical_check_kernel, grid_for(ctx, nmajor * 32), 256, 0, s, st->offsets->as<int64_t>(), st->indices->as<uint32_t>(), nmajor, nnz, flags->as<uint32_t>());

@@ -165,7 +165,63 @@ void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads
     });
 }
 
+// ---- count values: f32 -> u8 / u16 when that is lossless ------------------------------------------------------------
+// Raw counts are small non-negative integers stored as f32 (the common h5ad case). A chunk whose every value is an
+// integer in [0, 2^(8 dw)) travels as dw-byte integers. The test is bit-exact — the round trip through int32 must
+// reproduce the f32 bit pattern, so -0.0, NaN, fractions and negatives all refuse — and written on the bit patterns
+// without float compares so it vectorises: for a non-negative finite f32 the pattern is monotone in the value, hence
+// "negative, NaN, inf or >= 65536" is one unsigned comparison against 0x477FFFFF (65535.996); such lanes are zeroed
+// before the (then always defined) float -> int conversion and flagged.
+#define SRB_PACK_VALUES_LOOP(NAME, DST)                                                                             \
+    SRB_ISA_CLONES static uint32_t NAME(const float *__restrict__ s, DST *__restrict__ d, uint64_t n) {             \
+        uint32_t bad = 0, range = 0;                                                                                \
+        for (uint64_t i = 0; i < n; ++i) {                                                                          \
+            uint32_t bits, bbits;                                                                                   \
+            memcpy(&bits, s + i, 4);                                                                                \
+            const uint32_t m = (uint32_t)((int32_t)(0x477FFFFFu - bits) >> 31);                                     \
+            const uint32_t sb = bits & ~m;                                                                          \
+            float c;                                                                                                \
+            memcpy(&c, &sb, 4);                                                                                     \
+            const int32_t q = (int32_t)c;                                                                           \
+            const float back = (float)q;                                                                            \
+            memcpy(&bbits, &back, 4);                                                                               \
+            bad |= (bits ^ bbits) | m;                                                                              \
+            range |= (uint32_t)q;                                                                                   \
+            d[i] = (DST)q;                                                                                          \
+        }                                                                                                           \
+        return bad | (range >> (8 * sizeof(DST)));                                                                  \
+    }
+SRB_PACK_VALUES_LOOP(pack_f32_u8, uint8_t)
+SRB_PACK_VALUES_LOOP(pack_f32_u16, uint16_t)
+
+bool host_pack_values_f32(const float *src, uint64_t n, void *dst, int dst_width, int nthreads) {
+    if (n == 0) return true;
+    if (nthreads <= 0) nthreads = host_pack_threads();
+    const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads, n >> 16));
+    auto one = [&](uint64_t a, uint64_t b) -> uint32_t {
+        return dst_width == 1 ? pack_f32_u8(src + a, (uint8_t *)dst + a, b - a) : pack_f32_u16(src + a, (uint16_t *)dst + a, b - a);
+    };
+    if (parts == 1) return one(0, n) == 0;
+    std::vector<uint32_t> bad((size_t)parts, 0);
+    const uint64_t per = ((n + parts - 1) / parts + 63) & ~uint64_t(63);
+    pool().run(parts, [&](int p) {
+        const uint64_t a = std::min<uint64_t>(n, per * (uint64_t)p), b = std::min<uint64_t>(n, a + per);
+        if (b > a) bad[(size_t)p] = one(a, b);
+    });
+    uint32_t all = 0;
+    for (uint32_t v : bad) all |= v;
+    return all == 0;
+}
+
 }  // namespace srb
+
+extern "C" int32_t srb_host_pack_values_f32(const float *src, uint64_t n, void *dst, int32_t dst_width, int32_t nthreads,
+                                            int32_t *lossless) {
+    if ((n && (!src || !dst)) || (dst_width != 1 && dst_width != 2)) return -1;
+    const bool ok = srb::host_pack_values_f32(src, n, dst, dst_width, nthreads);
+    if (lossless) *lossless = ok ? 1 : 0;
+    return 0;
+}
 
 extern "C" int32_t srb_host_pack_indices(const void *src, int32_t src_width, uint64_t n, void *dst, int32_t dst_width,
                                          uint64_t bound, int32_t nthreads, int32_t *out_of_bounds) {

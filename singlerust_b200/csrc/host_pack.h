@@ -8,6 +8,9 @@ int host_pack_threads();
 // dst[i] = (narrow) src[i] for i < n, src entries `src_width` (4|8) bytes, dst entries `dst_width` (2|4) bytes;
 // returns true when any source value is >= bound. nthreads <= 0: the default.
 bool host_pack_indices(const void *src, int src_width, uint64_t n, void *dst, int dst_width, uint64_t bound, int nthreads);
+// dst[i] = (u8 | u16) src[i] when EVERY src[i] is an integer in [0, 2^(8 dst_width)) with the exact f32 bit pattern of
+// that integer (so the device can rebuild the f32 array bit for bit); returns false otherwise (dst is then garbage)
+bool host_pack_values_f32(const float *src, uint64_t n, void *dst, int dst_width, int nthreads);
 // threaded memcpy (pageable host memory -> pinned staging ring)
 void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads);
 }  // namespace srb

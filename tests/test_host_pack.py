@@ -44,3 +44,30 @@ def test_bad_arguments():
     assert lib.srb_host_pack_indices(_ffi._ptr(a), 3, 4, _ffi._ptr(a), 2, 10, 1, None) == -1
     assert lib.srb_host_pack_indices(_ffi._ptr(a), 8, 4, _ffi._ptr(a), 8, 10, 1, None) == -1
     assert lib.srb_host_pack_indices(None, 8, 4, _ffi._ptr(a), 2, 10, 1, None) == -1
+
+
+@pytest.mark.parametrize("dst_width", [1, 2])
+@pytest.mark.parametrize("n", [0, 1, 65, 3 * 65536 + 17, 2_500_000])
+def test_value_pack_round_trips_counts(dst_width, n):
+    rng = np.random.default_rng(n + dst_width)
+    hi = 256 if dst_width == 1 else 65536
+    v = rng.integers(0, hi, size=n).astype(np.float32)
+    if n:
+        v[-1] = hi - 1
+    d, ok = _ffi.host_pack_values_f32(v, dst_width)
+    assert ok
+    np.testing.assert_array_equal(d.astype(np.float32).view(np.uint32), v.view(np.uint32))  # bit for bit
+
+
+@pytest.mark.parametrize("bad", [0.5, -1.0, -0.0, np.nan, np.inf, -np.inf, 65536.0, 65535.5, 1e30, -1e30, 3.0000002, 1e-45])
+def test_value_pack_refuses_anything_lossy(bad):
+    n = 300_000
+    v = np.random.default_rng(3).integers(0, 200, size=n).astype(np.float32)
+    for pos in (0, n // 2 + 3, n - 1):
+        x = v.copy()
+        x[pos] = bad
+        assert _ffi.host_pack_values_f32(x, 1)[1] is False
+        assert _ffi.host_pack_values_f32(x, 2)[1] is False
+    x = v.copy()
+    x[7] = 256.0
+    assert _ffi.host_pack_values_f32(x, 1)[1] is False and _ffi.host_pack_values_f32(x, 2)[1] is True

@@ -126,3 +126,40 @@ def test_chunk_stream_in_pack_mode(ffi, ctxs):
     np.testing.assert_array_equal(st.number(ffi.COLUMN), O.number(cpu, O.COLUMN))
     np.testing.assert_array_equal(st.sum(ffi.ROW), O.sum_(cpu, O.ROW))
     st.free()
+
+
+@pytest.mark.parametrize("kind", ["u8", "u16", "fraction_late", "negative_zero", "mixed_widths"])
+def test_value_packing_is_lossless(ffi, ctxs, kind):
+    """f32 values travel as u8 / u16 per chunk when every value of the chunk is such an integer; anything else goes raw.
+    9 M entries = 3 chunks, so a late chunk can refuse after earlier ones were packed."""
+    n, m, per = 30_000, 30_000, 300
+    rng = np.random.default_rng(5)
+    cols = np.sort(rng.integers(0, m // per, size=(n, per)) + np.arange(per) * (m // per), axis=1)
+    nnz = n * per
+    val = rng.integers(1, 200, nnz).astype(np.float32)
+    if kind == "u16":
+        val[nnz // 3] = 40_000
+    elif kind == "fraction_late":
+        val[nnz - 5] = 2.5
+    elif kind == "negative_zero":
+        val[17] = -0.0
+    elif kind == "mixed_widths":
+        val[nnz // 2] = 300      # second chunk needs u16
+        val[nnz - 9] = 70_000    # last chunk goes raw
+    off = np.arange(0, nnz + 1, per, dtype=np.uint64)
+    idx = cols.ravel().astype(np.uint64)
+    ma = ffi.DeviceMatrix.upload(ctxs[0], ffi.CSR, n, m, off, idx, val)
+    mb = ffi.DeviceMatrix.upload(ctxs[1], ffi.CSR, n, m, off, idx, val)
+    va, vb = ma.download(values="f32")[2], mb.download(values="f32")[2]
+    np.testing.assert_array_equal(vb.view(np.uint32), val.view(np.uint32))   # bit for bit, including -0.0
+    np.testing.assert_array_equal(va.view(np.uint32), vb.view(np.uint32))
+    h2d, packed = ctxs[1].last_upload()
+    assert packed
+    raw = 8 * (n + 1) + 2 * nnz + 4 * nnz
+    if kind == "u8":
+        assert h2d == 8 * (n + 1) + 2 * nnz + nnz
+    elif kind in ("fraction_late", "mixed_widths", "u16"):
+        assert 8 * (n + 1) + 3 * nnz < h2d < raw
+    else:
+        assert h2d == raw
+    np.testing.assert_array_equal(ma.sum(ffi.ROW), mb.sum(ffi.ROW))
