@@ -61,12 +61,16 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *   DEVICE_NARROW  copy the host integers as they are (8 bytes per entry for Rust usize) and narrow on the device
  *   HOST_PACK      narrow on the host (thread pool, pinned staging ring) to 2 bytes per entry when the minor dimension
  *                  is <= 65 536, else 4, overlap packing with the DMA, and stage pageable caller memory (a Rust Vec)
- *                  through the same ring; f32 values travel as u8 / u16 for every chunk in which that is lossless
- *                  (raw counts), bit-identical f32 on the device (SRB_UPLOAD_PACK_VALUES=0 disables)
+ *                  through the same ring
+ *   HOST_PACK_VALUES  HOST_PACK, and f32 values travel as u8 / u16 for every chunk in which that is lossless (raw
+ *                  counts; bit-identical f32 on the device). Pays only when the link, not the host, is the bottleneck:
+ *                  on the 16-core bench host it is slower than HOST_PACK (measured, profiles/), so AUTO never picks it
  *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
  *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
- * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto) overrides it. */
-typedef enum srb_upload_mode { SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2 } srb_upload_mode;
+ * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values) overrides it. */
+typedef enum srb_upload_mode {
+    SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2, SRB_UPLOAD_HOST_PACK_VALUES = 3
+} srb_upload_mode;
 
 typedef struct srb_ctx srb_ctx;
 typedef struct srb_mat srb_mat;

@@ -230,6 +230,7 @@ static int upload_pack_mode() {
         const char *e = getenv("SRB_UPLOAD_PACK");
         if (!e) v = SRB_UPLOAD_DEFAULT_MODE;
         else if (!strcmp(e, "auto")) v = SRB_UPLOAD_AUTO;
+        else if (!strcmp(e, "values")) v = SRB_UPLOAD_HOST_PACK_VALUES;
         else v = atoi(e) != 0 ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
     }
     return v;
@@ -238,10 +239,10 @@ static int upload_pack_mode() {
 static int upload_threads(const srb_ctx *c) { return std::max(1, host_pack_threads() / std::max(1, c->nranks)); }
 // AUTO: packing pays when the host narrows faster than the link moves the unpacked array (12 B per entry at ~55 GB/s =
 // 4.6 G entries/s; one host thread packs ~0.9 G entries/s), i.e. with >= 6 threads, and only for arrays worth a ring
-static bool use_packed_upload(const srb_ctx *c, uint64_t nnz) {
+static int effective_upload_mode(const srb_ctx *c, uint64_t nnz) {
     const int mode = c->upload_mode >= 0 ? c->upload_mode : upload_pack_mode();
-    if (mode == SRB_UPLOAD_AUTO) return nnz >= (1ull << 20) && upload_threads(c) >= 6;
-    return mode == SRB_UPLOAD_HOST_PACK;
+    if (mode == SRB_UPLOAD_AUTO) return (nnz >= (1ull << 20) && upload_threads(c) >= 6) ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
+    return mode;
 }
 static bool host_is_pageable(const void *p) {
     cudaPointerAttributes a;
@@ -274,24 +275,16 @@ __global__ void unpack_values_kernel(const uint8_t *__restrict__ pk, float *__re
         else if (w == 2) out[i] = (float)reinterpret_cast<const uint16_t *>(pk)[i];
     }
 }
-static bool upload_pack_values() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("SRB_UPLOAD_PACK_VALUES");
-        v = e ? (atoi(e) != 0) : 1;
-    }
-    return v == 1;
-}
 // indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too.
 // Returns the bytes that crossed the link.
 static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
-                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val) {
+                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val, bool want_value_packing) {
     if (n == 0) return 0;
     cudaStream_t s = c->stream;
     const int pw = bound <= 65536 ? 2 : 4;
     const int nthreads = upload_threads(c);
     const bool stage_vals = values && host_is_pageable(values);
-    const bool pack_vals = values && vsz == 4 && upload_pack_values();  // f32 counts -> u8 / u16 where lossless
+    const bool pack_vals = values && vsz == 4 && want_value_packing;  // f32 counts -> u8 / u16 where lossless
     constexpr int kChunkShift = 22;
     const uint64_t chunk = std::min<uint64_t>(n, 1ull << kChunkShift);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
@@ -480,7 +473,8 @@ int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode) {
 int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
     SRB_API_BEGIN
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
-    SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO, SRB_ERR_INVALID_ARG, "bad upload mode");
+    SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO ||
+                    mode == SRB_UPLOAD_HOST_PACK_VALUES, SRB_ERR_INVALID_ARG, "bad upload mode");
     ctx->upload_mode = mode;
     SRB_API_END
 }
@@ -527,7 +521,8 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     } else {
         upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
     }
-    const bool packed = use_packed_upload(ctx, nnz);
+    const int up_mode = effective_upload_mode(ctx, nnz);
+    const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES;
     if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
     std::unique_ptr<srb_mat> m(new srb_mat());
     m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
@@ -541,7 +536,7 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     uint64_t link_bytes = 0;
     if (packed)
         link_bytes = upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
-                                   direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p);
+                                   direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p, up_mode == SRB_UPLOAD_HOST_PACK_VALUES);
     if (!(packed && direct)) {
         if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
         else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());

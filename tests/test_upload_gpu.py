@@ -19,12 +19,14 @@ def ffi():
 
 @pytest.fixture(scope="module")
 def ctxs(ffi):
-    a, b = ffi.Context(0), ffi.Context(0)
+    a, b, c = ffi.Context(0), ffi.Context(0), ffi.Context(0)
     a.set_upload_mode(ffi.UPLOAD_DEVICE_NARROW)
     b.set_upload_mode(ffi.UPLOAD_HOST_PACK)
-    yield a, b
+    c.set_upload_mode(ffi.UPLOAD_HOST_PACK_VALUES)
+    yield a, b, c
     a.close()
     b.close()
+    c.close()
 
 
 def same_matrix(ma, mb):
@@ -71,7 +73,7 @@ def test_out_of_bounds_index_is_reported(ffi, ctxs, bound_case):
     a = random_csr(np.random.default_rng(1), 20, 10, 0.3)
     bad = a.indices.astype(np.uint64).copy()
     bad[3] = ncols
-    for ctx in ctxs:
+    for ctx in ctxs[:2]:
         with pytest.raises(ffi.SrbError) as e:
             ffi.DeviceMatrix.upload(ctx, ffi.CSR, 20, ncols, a.indptr.astype(np.uint64), bad, a.data)
         assert e.value.code == -3
@@ -149,11 +151,11 @@ def test_value_packing_is_lossless(ffi, ctxs, kind):
     off = np.arange(0, nnz + 1, per, dtype=np.uint64)
     idx = cols.ravel().astype(np.uint64)
     ma = ffi.DeviceMatrix.upload(ctxs[0], ffi.CSR, n, m, off, idx, val)
-    mb = ffi.DeviceMatrix.upload(ctxs[1], ffi.CSR, n, m, off, idx, val)
+    mb = ffi.DeviceMatrix.upload(ctxs[2], ffi.CSR, n, m, off, idx, val)
     va, vb = ma.download(values="f32")[2], mb.download(values="f32")[2]
     np.testing.assert_array_equal(vb.view(np.uint32), val.view(np.uint32))   # bit for bit, including -0.0
     np.testing.assert_array_equal(va.view(np.uint32), vb.view(np.uint32))
-    h2d, packed = ctxs[1].last_upload()
+    h2d, packed = ctxs[2].last_upload()
     assert packed
     raw = 8 * (n + 1) + 2 * nnz + 4 * nnz
     if kind == "u8":
