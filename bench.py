@@ -324,6 +324,16 @@ def run_ours(args):
                         "executed_tflops": ex, "frac_executed": ex / tf_sust,
                         "note": "algorithmic = SYRK n*d^2; executed = split-fp16 x3 on upper-triangular 256x256 pair tiles "
                                 "(tcgen05 cta_group::2); peak = sustained (power-capped) dense bf16"}
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/), only for the exact config it was taken on
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic_L.json")) as f:
+            tr = json.load(f)
+        if tr["config"] == {"cells_per_gpu": args.cells, "genes": args.genes, "hvg": args.hvg, "pcs": args.pcs}:
+            for k, b in tr["traffic_bytes"].items():
+                if k in roof:
+                    roof[k]["traffic"] = b
+    except (OSError, KeyError, ValueError):
+        pass
     dominant = max(roof, key=lambda k: roof[k]["ms"]) if roof else None
 
     line = {
