@@ -72,6 +72,14 @@ typedef enum srb_upload_mode {
     SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2, SRB_UPLOAD_HOST_PACK_VALUES = 3
 } srb_upload_mode;
 
+/* K8, the eigensolver behind srb_pca (top-k eigenpairs of the n_sel x n_sel correlation matrix):
+ *   SYEVD  cuSOLVER's full fp64 divide-and-conquer solver (28 ms at n_sel = 2000: latency-bound tridiagonalisation)
+ *   CHFSI  Chebyshev-filtered subspace iteration for the k leading pairs, built from fp64 GEMMs (csrc/eig.cu); used when
+ *          n_sel >= 1024 and 8 k <= n_sel, converged to ||C v - theta v|| <= 1e-11 |theta_1|, and falls back to SYEVD on
+ *          any doubt (breakdown, non-finite values, no convergence)
+ * Process default: environment SRB_EIG_MODE (syevd | chfsi). */
+typedef enum srb_eig_mode { SRB_EIG_SYEVD = 0, SRB_EIG_CHFSI = 1 } srb_eig_mode;
+
 typedef struct srb_ctx srb_ctx;
 typedef struct srb_mat srb_mat;
 
@@ -97,6 +105,11 @@ int32_t srb_ctx_create(int32_t device, srb_ctx **out);
 int32_t srb_ctx_destroy(srb_ctx *ctx);
 int32_t srb_ctx_set_value_mode(srb_ctx *ctx, int32_t mode /* srb_value_mode */);
 int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode /* srb_upload_mode */);
+int32_t srb_ctx_set_eig_mode(srb_ctx *ctx, int32_t mode /* srb_eig_mode */);
+/* what K8 did in the last srb_pca / srb_pipeline_* call on this ctx: solver = 0 SYEVD, 1 CHFSI, 2 CHFSI fell back to SYEVD;
+ * for CHFSI the number of d x b block products (DGEMMs), outer (Rayleigh-Ritz) iterations and the final
+ * max ||C v - theta v|| / |theta_1| over the k pairs. Any pointer may be NULL. */
+int32_t srb_ctx_last_eig(srb_ctx *ctx, int32_t *solver, int32_t *block_products, int32_t *outer_iterations, double *max_residual);
 /* what the last srb_mat_upload on this ctx moved over the link: bytes, and whether the index array was host-packed */
 int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_packed);
 int32_t srb_ctx_synchronize(srb_ctx *ctx);

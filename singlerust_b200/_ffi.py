@@ -14,6 +14,7 @@ ROW, COLUMN = 0, 1
 CSR, CSC = 0, 1
 VALUES_COMPACT, VALUES_FAITHFUL = 0, 1
 GRAM_TENSOR, GRAM_FP64 = 0, 1
+EIG_SYEVD, EIG_CHFSI = 0, 1
 UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK, UPLOAD_AUTO, UPLOAD_HOST_PACK_VALUES = 0, 1, 2, 3
 
 DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
@@ -55,6 +56,8 @@ def lib() -> C.CDLL:
             "srb_ctx_set_upload_mode": [vp, i32],
             "srb_host_pack_indices": [vp, i32, u64, vp, i32, u64, i32, C.POINTER(i32)],
             "srb_ctx_last_upload": [vp, C.POINTER(u64), C.POINTER(i32)],
+            "srb_ctx_set_eig_mode": [vp, i32],
+            "srb_ctx_last_eig": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f64)],
             "srb_host_pack_values_f32": [vp, u64, vp, i32, i32, C.POINTER(i32)],
             "srb_ctx_synchronize": [vp],
             "srb_comm_unique_id": [vp],
@@ -162,6 +165,16 @@ class Context:
 
     def set_upload_mode(self, mode):
         check(lib().srb_ctx_set_upload_mode(self._h, mode))
+
+    def set_eig_mode(self, mode):
+        check(lib().srb_ctx_set_eig_mode(self._h, mode))
+
+    def last_eig(self):
+        """dict(solver 'syevd' | 'chfsi' | 'chfsi->syevd', block_products, outer_iterations, max_residual) of the last K8."""
+        s, p, o, r = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        check(lib().srb_ctx_last_eig(self._h, C.byref(s), C.byref(p), C.byref(o), C.byref(r)))
+        return dict(solver=("syevd", "chfsi", "chfsi->syevd")[s.value], block_products=p.value, outer_iterations=o.value,
+                    max_residual=r.value)
 
     def last_upload(self):
         """(bytes the last upload moved over the link, index array was host-packed)"""

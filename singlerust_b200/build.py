@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [os.path.join(objdir, src.replace(".cu", ".o")) for src in SOURCES]
     objs += [os.path.join(objdir, src.replace(".cpp", ".o")) for src in HOST_SOURCES]
     if force or jobs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-lcusolver", "-lcuda", "-ldl", "-lpthread",
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-lcusolver", "-lcublas", "-lcuda", "-ldl", "-lpthread",
                                                       "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -479,6 +479,24 @@ int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
     SRB_API_END
 }
 
+int32_t srb_ctx_set_eig_mode(srb_ctx *ctx, int32_t mode) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    SRB_REQUIRE(mode == SRB_EIG_SYEVD || mode == SRB_EIG_CHFSI, SRB_ERR_INVALID_ARG, "bad eig mode");
+    ctx->eig_mode = mode;
+    SRB_API_END
+}
+
+int32_t srb_ctx_last_eig(srb_ctx *ctx, int32_t *solver, int32_t *block_products, int32_t *outer_iterations, double *max_residual) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    if (solver) *solver = ctx->last_eig_mode;
+    if (block_products) *block_products = ctx->last_eig_products;
+    if (outer_iterations) *outer_iterations = ctx->last_eig_outer;
+    if (max_residual) *max_residual = ctx->last_eig_residual;
+    SRB_API_END
+}
+
 int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_packed) {
     SRB_API_BEGIN
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");

@@ -103,6 +103,10 @@ struct srb_ctx {
     // cuSOLVER handle (lazy, eig.cu) and the high-priority side stream its small latency-bound kernels run on, so
     // that they are scheduled ahead of another context's bandwidth-bound kernels when batches are pipelined
     void *solver = nullptr;
+    void *blas = nullptr;  // cublasHandle_t of the ChFSI eigensolver (lazy, eig.cu)
+    int eig_mode = -1;     // srb_eig_mode, -1 = the process default (SRB_EIG_MODE)
+    int last_eig_mode = 0, last_eig_products = 0, last_eig_outer = 0;  // what the last K8 did: 0 syevd, 1 chfsi, 2 chfsi fell back
+    double last_eig_residual = 0.0;
     void *solver_params = nullptr;
     cudaStream_t eig_stream = nullptr;
     cudaEvent_t eig_in = nullptr, eig_out = nullptr;
