@@ -341,7 +341,7 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 values / f64 accumulate (fp16x2-split tensor Gram)" if args.gram_mode == 0 else "f32 values / f64 accumulate",
         "data": "synthetic", "config": workload_config(args), "gpu_launches": int(launches), "clocks": clocks,
-        "nnz_per_gpu": int(nnz), "stage_ms": mean_stage, "peaks": peak_src,
+        "nnz_per_gpu": int(nnz), "stage_ms": mean_stage, "eig_solver": ctx.last_eig(), "peaks": peak_src,
         "roofline": dict(roof[dominant], kernel=dominant) if dominant else None,
         "rooflines": roof,
     }

@@ -77,7 +77,7 @@ typedef enum srb_upload_mode {
  *   CHFSI  Chebyshev-filtered subspace iteration for the k leading pairs, built from fp64 GEMMs (csrc/eig.cu); used when
  *          n_sel >= 1024 and 8 k <= n_sel, converged to ||C v - theta v|| <= 1e-11 |theta_1|, and falls back to SYEVD on
  *          any doubt (breakdown, non-finite values, no convergence)
- * Process default: environment SRB_EIG_MODE (syevd | chfsi). */
+ * Process default: CHFSI; environment SRB_EIG_MODE (syevd | chfsi) overrides it. */
 typedef enum srb_eig_mode { SRB_EIG_SYEVD = 0, SRB_EIG_CHFSI = 1 } srb_eig_mode;
 
 typedef struct srb_ctx srb_ctx;
