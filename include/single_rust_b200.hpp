@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -608,6 +609,174 @@ public:
                         off.data(), m_.indices + base, m_.values + base};
             f(c);
         }
+    }
+};
+
+// ---- on-disk chunk store -----------------------------------------------------------------------------------------------
+// A directory with meta.txt ("csr|csc nrows ncols"), indptr.npy, indices.npy, data.npy — the three arrays an .h5ad X group
+// holds (there is no HDF5 library in this image). Written by singlerust_b200.anndata.BackedAnnData.write_store or
+// write_store() below; chunks are read with fseek/fread only when the iterator reaches them.
+namespace store_detail {
+struct NpyInfo {
+    std::string descr;     // e.g. "<f4", "<u8"
+    uint64_t count = 0;    // elements (1-D arrays only)
+    long long offset = 0;  // byte offset of the data
+};
+inline NpyInfo npy_header(const std::string &path) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw Error(SRB_ERR_INVALID_ARG, "cannot open " + path);
+    unsigned char pre[12];
+    NpyInfo info;
+    bool ok = std::fread(pre, 1, 10, f) == 10 && std::memcmp(pre, "\x93NUMPY", 6) == 0;
+    size_t hlen = 0;
+    if (ok && pre[6] == 1) {
+        hlen = pre[8] | (size_t)pre[9] << 8;
+        info.offset = 10;
+    } else if (ok && (pre[6] == 2 || pre[6] == 3)) {
+        ok = std::fread(pre + 10, 1, 2, f) == 2;
+        hlen = pre[8] | (size_t)pre[9] << 8 | (size_t)pre[10] << 16 | (size_t)pre[11] << 24;
+        info.offset = 12;
+    } else {
+        ok = false;
+    }
+    std::string h(hlen, ' ');
+    ok = ok && std::fread(&h[0], 1, hlen, f) == hlen;
+    std::fclose(f);
+    if (!ok) throw Error(SRB_ERR_INVALID_ARG, path + ": not a .npy file");
+    info.offset += (long long)hlen;
+    const size_t d = h.find("'descr'"), fo = h.find("'fortran_order'"), sh = h.find("'shape'");
+    if (d == std::string::npos || sh == std::string::npos) throw Error(SRB_ERR_INVALID_ARG, path + ": unreadable .npy header");
+    const size_t q0 = h.find('\'', h.find(':', d)), q1 = h.find('\'', q0 + 1);
+    info.descr = h.substr(q0 + 1, q1 - q0 - 1);
+    if (fo != std::string::npos && h.compare(h.find(':', fo) + 1, 5, " True") == 0) throw Error(SRB_ERR_UNSUPPORTED, path + ": fortran order");
+    const size_t p0 = h.find('(', sh), p1 = h.find(')', p0);
+    const std::string shape = h.substr(p0 + 1, p1 - p0 - 1);
+    if (std::count(shape.begin(), shape.end(), ',') > 1) throw Error(SRB_ERR_UNSUPPORTED, path + ": not one-dimensional");
+    info.count = shape.find_first_of("0123456789") == std::string::npos ? 0 : std::stoull(shape);
+    return info;
+}
+inline void read_at(const std::string &path, long long offset, void *dst, size_t bytes) {
+    if (!bytes) return;
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) throw Error(SRB_ERR_INVALID_ARG, "cannot open " + path);
+    const bool ok = fseeko(f, (off_t)offset, SEEK_SET) == 0 && std::fread(dst, 1, bytes, f) == bytes;
+    std::fclose(f);
+    if (!ok) throw Error(SRB_ERR_INVALID_ARG, "short read from " + path);
+}
+template <class T> struct npy_descr;
+#define SRB_HPP_DESCR(T, S) \
+    template <> struct npy_descr<T> { static const char *value() { return S; } }
+SRB_HPP_DESCR(int8_t, "|i1");
+SRB_HPP_DESCR(uint8_t, "|u1");
+SRB_HPP_DESCR(int16_t, "<i2");
+SRB_HPP_DESCR(uint16_t, "<u2");
+SRB_HPP_DESCR(int32_t, "<i4");
+SRB_HPP_DESCR(uint32_t, "<u4");
+SRB_HPP_DESCR(int64_t, "<i8");
+SRB_HPP_DESCR(uint64_t, "<u8");
+SRB_HPP_DESCR(float, "<f4");
+SRB_HPP_DESCR(double, "<f8");
+#undef SRB_HPP_DESCR
+template <class T>
+void write_npy(const std::string &path, const T *data, uint64_t n) {
+    std::string h = std::string("{'descr': '") + npy_descr<T>::value() + "', 'fortran_order': False, 'shape': (" + std::to_string(n) + ",), }";
+    while ((10 + h.size() + 1) % 64) h.push_back(' ');
+    h.push_back('\n');
+    FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) throw Error(SRB_ERR_INVALID_ARG, "cannot create " + path);
+    const unsigned char pre[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, (unsigned char)(h.size() & 255), (unsigned char)(h.size() >> 8)};
+    const bool ok = std::fwrite(pre, 1, 10, f) == 10 && std::fwrite(h.data(), 1, h.size(), f) == h.size() &&
+                    (n == 0 || std::fwrite(data, sizeof(T), n, f) == n);
+    std::fclose(f);
+    if (!ok) throw Error(SRB_ERR_INVALID_ARG, "short write to " + path);
+}
+}  // namespace store_detail
+
+template <class T>
+void write_store(const std::string &dir, const CsView<T> &m) {
+    FILE *f = std::fopen((dir + "/meta.txt").c_str(), "w");
+    if (!f) throw Error(SRB_ERR_INVALID_ARG, "cannot create " + dir + "/meta.txt (the directory must exist)");
+    std::fprintf(f, "%s %llu %llu\n", m.format == Format::Csr ? "csr" : "csc", (unsigned long long)m.nrows, (unsigned long long)m.ncols);
+    std::fclose(f);
+    store_detail::write_npy(dir + "/indptr.npy", m.offsets, m.nmajor() + 1);
+    store_detail::write_npy(dir + "/indices.npy", m.indices, m.nnz());
+    store_detail::write_npy(dir + "/data.npy", m.values, m.nnz());
+}
+
+/// ChunkSource over an on-disk chunk store: only indptr is held in memory; index / value chunks are read on demand.
+template <class T>
+class StoreChunkSource : public ChunkSource<T> {
+    std::string dir_;
+    Format format_ = Format::Csr;
+    uint64_t nrows_ = 0, ncols_ = 0;
+    std::vector<uint64_t> indptr_;
+    store_detail::NpyInfo idx_, val_;
+    mutable CsMatrix<T> whole_;  // filled by whole()
+
+    void read_lines(uint64_t s, uint64_t e, std::vector<uint64_t> &off, std::vector<uint64_t> &idx, std::vector<T> &val) const {
+        const uint64_t a = indptr_[s], b = indptr_[e], n = b - a;
+        off.resize(e - s + 1);
+        for (uint64_t i = s; i <= e; ++i) off[i - s] = indptr_[i] - a;
+        idx.resize(n), val.resize(n);
+        if (idx_.descr == "<u8" || idx_.descr == "<i8") {
+            store_detail::read_at(dir_ + "/indices.npy", idx_.offset + (long long)(8 * a), idx.data(), 8 * n);
+        } else {  // 4-byte on-disk indices (the h5ad convention) are widened to the usize layout
+            std::vector<uint32_t> tmp(n);
+            store_detail::read_at(dir_ + "/indices.npy", idx_.offset + (long long)(4 * a), tmp.data(), 4 * n);
+            std::copy(tmp.begin(), tmp.end(), idx.begin());
+        }
+        store_detail::read_at(dir_ + "/data.npy", val_.offset + (long long)(sizeof(T) * a), val.data(), sizeof(T) * n);
+    }
+
+public:
+    explicit StoreChunkSource(const std::string &dir) : dir_(dir) {
+        FILE *f = std::fopen((dir + "/meta.txt").c_str(), "r");
+        if (!f) throw Error(SRB_ERR_INVALID_ARG, "cannot open " + dir + "/meta.txt");
+        char fmt[8] = {0};
+        unsigned long long r = 0, c = 0;
+        const int got = std::fscanf(f, "%7s %llu %llu", fmt, &r, &c);
+        std::fclose(f);
+        if (got != 3 || (std::strcmp(fmt, "csr") && std::strcmp(fmt, "csc"))) throw Error(SRB_ERR_INVALID_ARG, dir + "/meta.txt: expected 'csr|csc nrows ncols'");
+        format_ = std::strcmp(fmt, "csr") ? Format::Csc : Format::Csr, nrows_ = r, ncols_ = c;
+        const store_detail::NpyInfo ip = store_detail::npy_header(dir + "/indptr.npy");
+        idx_ = store_detail::npy_header(dir + "/indices.npy"), val_ = store_detail::npy_header(dir + "/data.npy");
+        const uint64_t nmajor = format_ == Format::Csr ? nrows_ : ncols_;
+        if (ip.count != nmajor + 1 || idx_.count != val_.count) throw Error(SRB_ERR_INVALID_ARG, dir + ": arrays do not match meta.txt");
+        if (val_.descr != store_detail::npy_descr<T>::value()) throw Error(SRB_ERR_UNSUPPORTED_DTYPE, dir + "/data.npy holds " + val_.descr + ", not " + store_detail::npy_descr<T>::value());
+        if (idx_.descr != "<u8" && idx_.descr != "<i8" && idx_.descr != "<u4" && idx_.descr != "<i4") throw Error(SRB_ERR_UNSUPPORTED_DTYPE, dir + "/indices.npy: " + idx_.descr);
+        indptr_.resize(nmajor + 1);
+        if (ip.descr == "<u8" || ip.descr == "<i8") {
+            store_detail::read_at(dir + "/indptr.npy", ip.offset, indptr_.data(), 8 * (nmajor + 1));
+        } else if (ip.descr == "<u4" || ip.descr == "<i4") {
+            std::vector<uint32_t> tmp(nmajor + 1);
+            store_detail::read_at(dir + "/indptr.npy", ip.offset, tmp.data(), 4 * (nmajor + 1));
+            std::copy(tmp.begin(), tmp.end(), indptr_.begin());
+        } else {
+            throw Error(SRB_ERR_UNSUPPORTED_DTYPE, dir + "/indptr.npy: " + ip.descr);
+        }
+        if (indptr_.front() != 0 || indptr_.back() != idx_.count) throw Error(SRB_ERR_INVALID_ARG, dir + ": indptr does not span the index array");
+    }
+    uint64_t n_obs() const override { return nrows_; }
+    uint64_t n_vars() const override { return ncols_; }
+    Format format() const override { return format_; }
+    void for_each_chunk(size_t chunk_size, const std::function<void(const CsView<T> &)> &f) const override {
+        if (chunk_size == 0) throw Error(SRB_ERR_INVALID_ARG, "chunk size must be positive");
+        const uint64_t nmajor = indptr_.size() - 1;
+        std::vector<uint64_t> off, idx;
+        std::vector<T> val;
+        for (uint64_t s = 0; s < nmajor; s += chunk_size) {
+            const uint64_t e = std::min<uint64_t>(nmajor, s + chunk_size);
+            read_lines(s, e, off, idx, val);
+            f(CsView<T>{format_, format_ == Format::Csr ? e - s : nrows_, format_ == Format::Csr ? ncols_ : e - s, off.data(), idx.data(), val.data()});
+        }
+    }
+    /// reads the whole matrix into memory (ComputationMode::Whole)
+    CsView<T> whole() const override {
+        if (whole_.offsets.empty()) {
+            whole_.format = format_, whole_.nrows = nrows_, whole_.ncols = ncols_;
+            read_lines(0, indptr_.size() - 1, whole_.offsets, whole_.indices, whole_.values);
+        }
+        return whole_.view();
     }
 };
 

@@ -85,7 +85,7 @@ static CsMatrix<float> random_csr(uint64_t n, uint64_t m, double density, uint64
     return a;
 }
 
-static int cpu_check() {
+static int cpu_check(const char *store_dir) {
     // (1) no device: construction fails loudly, nothing falls back to the CPU
     bool threw = false;
     try {
@@ -135,6 +135,40 @@ static int cpu_check() {
         rows += c.nrows, nnz += c.nnz(), ++calls;
     });
     CHECK(rows == 4 && nnz == 8 && calls == 2);
+    // (3b) the on-disk chunk store: write, reopen, iterate — every chunk equals the in-memory iterator's
+    if (store_dir) {
+        CsMatrix<float> a = random_csr(257, 61, 0.2, 7);
+        backed::write_store(store_dir, a.view());
+        backed::StoreChunkSource<float> disk(store_dir);
+        backed::HostChunkSource<float> mem(a.view());
+        CHECK(disk.n_obs() == 257 && disk.n_vars() == 61 && disk.format() == Format::Csr);
+        for (size_t chunk : {1u, 50u, 256u, 257u, 1000u}) {
+            std::vector<std::vector<uint64_t>> offs, idxs;
+            std::vector<std::vector<float>> vals;
+            mem.for_each_chunk(chunk, [&](const CsView<float> &c) {
+                offs.emplace_back(c.offsets, c.offsets + c.nmajor() + 1);
+                idxs.emplace_back(c.indices, c.indices + c.nnz());
+                vals.emplace_back(c.values, c.values + c.nnz());
+            });
+            size_t i = 0;
+            disk.for_each_chunk(chunk, [&](const CsView<float> &c) {
+                CHECK(i < offs.size() && c.ncols == 61 && c.nmajor() + 1 == offs[i].size());
+                CHECK(std::equal(offs[i].begin(), offs[i].end(), c.offsets) && std::equal(idxs[i].begin(), idxs[i].end(), c.indices) &&
+                      std::equal(vals[i].begin(), vals[i].end(), c.values));
+                ++i;
+            });
+            CHECK(i == offs.size());
+        }
+        CsView<float> w = disk.whole();
+        CHECK(w.nnz() == a.indices.size() && std::equal(a.values.begin(), a.values.end(), w.values));
+        bool wrong_dtype = false;
+        try {
+            backed::StoreChunkSource<double> bad(store_dir);
+        } catch (const Error &e) {
+            wrong_dtype = e.code == SRB_ERR_UNSUPPORTED_DTYPE;
+        }
+        CHECK(wrong_dtype);
+    }
     // (4) vocabulary
     CHECK((int32_t)Direction::Row == 0 && (int32_t)Direction::Column == 1 && shared::is_row(Direction::Row));
     CHECK(ComputationMode::Whole().is_whole() && !ComputationMode::Chunked(7).is_whole() && *ComputationMode::Chunked(7).chunk == 7);
@@ -329,7 +363,17 @@ static void random_checks(Device &dev, Device &faithful) {
 }
 
 int main(int argc, char **argv) {
-    if (argc > 1 && std::string(argv[1]) == "--cpu-check") return cpu_check();
+    if (argc > 1 && std::string(argv[1]) == "--cpu-check") return cpu_check(argc > 2 ? argv[2] : nullptr);
+    if (argc > 3 && std::string(argv[1]) == "--store-sums") {  // per-chunk value sums of a chunk store written by someone else
+        backed::StoreChunkSource<float> disk(argv[2]);
+        disk.for_each_chunk((size_t)std::atoll(argv[3]), [&](const CsView<float> &c) {
+            double s = 0;
+            uint64_t is = 0;
+            for (uint64_t i = 0; i < c.nnz(); ++i) s += c.values[i], is += c.indices[i];
+            printf("%llu %llu %.17g %llu\n", (unsigned long long)c.nmajor(), (unsigned long long)c.nnz(), s, (unsigned long long)is);
+        });
+        return 0;
+    }
     try {
         Device dev(0), faithful(0, SRB_VALUES_FAITHFUL);
         kat_checks(dev, faithful);

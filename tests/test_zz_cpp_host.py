@@ -34,9 +34,36 @@ def test_cpp_host_compiles_and_fails_loudly_without_a_gpu():
     exe = build_exe()
     if torch.cuda.is_available():
         pytest.skip("a GPU is present: the no-device behaviour is checked on the CPU box")
-    r = subprocess.run([exe, "--cpu-check"], capture_output=True, text=True, timeout=120)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        r = subprocess.run([exe, "--cpu-check", d], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 failed" in r.stdout
+
+
+@pytest.mark.parametrize("index_dtype", ["uint64", "uint32"])
+def test_cpp_reads_the_chunk_store_python_writes(index_dtype):
+    """One on-disk format for both host sides: BackedAnnData.write_store (Python) -> StoreChunkSource (C++)."""
+    import tempfile
+
+    import numpy as np
+
+    from singlerust_b200.anndata import BackedAnnData
+    from tests._util import random_csr
+    exe = build_exe()
+    a = random_csr(np.random.default_rng(3), 500, 90, 0.1, empty_rows=(0, 499))
+    with tempfile.TemporaryDirectory() as d:
+        BackedAnnData.write_store(d, a, np.dtype(index_dtype))
+        r = subprocess.run([exe, "--store-sums", d, "128"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows = [line.split() for line in r.stdout.strip().splitlines()]
+        back = BackedAnnData.open_store(d)
+        want = [(ch.shape[0], ch.nnz, float(ch.data.astype(np.float64).sum()), int(ch.indices.astype(np.int64).sum()))
+                for ch, _s, _e in back.iter_chunks(128)]
+    assert len(rows) == len(want) == 4
+    for got, w in zip(rows, want):
+        assert (int(got[0]), int(got[1]), int(got[3])) == (w[0], w[1], w[3])
+        assert float(got[2]) == w[2]
 
 
 @pytest.mark.gpu
