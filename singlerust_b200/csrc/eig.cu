@@ -165,10 +165,25 @@ struct ChfsiStats {
 // columns 0..k-1 of d_C hold the eigenvectors of the k largest eigenvalues in ASCENDING order and d_evals[0..k-1] the values.
 static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, cudaStream_t es, double *d_C, uint32_t d, uint32_t k,
                        double *d_evals) {
-    constexpr int L = 40;           // Krylov steps for the bounds
+    // tunables (round-2 sweeps without a rebuild; the defaults are the measured configuration):
+    //   SRB_CHFSI_KRYLOV  Krylov steps for the bounds (8..40, default 40)   SRB_CHFSI_BLOCK  block width b (multiple of 32)
+    //   SRB_CHFSI_TARGET  log10 of the gain of the k-th eigenvalue over the cut per outer round (default 11)
+    static const int L = [] {
+        const char *e = getenv("SRB_CHFSI_KRYLOV");
+        return e ? std::max(8, std::min(40, atoi(e))) : 40;
+    }();
+    static const uint32_t b_env = [] {
+        const char *e = getenv("SRB_CHFSI_BLOCK");
+        return e ? (uint32_t)std::max(0, atoi(e)) / 32 * 32 : 0u;
+    }();
+    static const double kTarget = [] {
+        const char *e = getenv("SRB_CHFSI_TARGET");
+        return std::pow(10.0, e ? std::max(6.0, std::min(14.0, atof(e))) : 11.0);
+    }();
     constexpr int kMaxOuter = 6, kMaxRounds = 24, kMaxDegree = 32;
-    constexpr double kAmpCap = 1e8, kTarget = 1e11, kTol = 1e-11;
-    const uint32_t b = std::min<uint32_t>(d / 4, ((std::max<uint32_t>(3 * k, k + 96) + 63) / 64) * 64);
+    constexpr double kAmpCap = 1e8, kTol = 1e-11;
+    uint32_t b = std::min<uint32_t>(d / 4, ((std::max<uint32_t>(3 * k, k + 96) + 63) / 64) * 64);
+    if (b_env >= k + 16 && b_env <= d / 2) b = b_env;
     if (b < k + 16 || d < 512) return false;
     const double one = 1.0, zero = 0.0, minus1 = -1.0;
     const size_t dd = (size_t)d * d, db = (size_t)d * b;
