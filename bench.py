@@ -134,6 +134,21 @@ def cpu_pipeline_once(sample, hvg, pcs):
     return time.perf_counter() - t0
 
 
+def cpu_pipeline_reference_faithful(sample, hvg, pcs):
+    """The same pipeline with the reference's own pass structure and threading: serial loops, f64 values
+    after normalise, three passes for the per-gene variance, map-based selected densify; only the SVD uses all cores
+    (the reference hands it to LAPACK / faer). Returns seconds."""
+    from oracle import oracle as O
+    from oracle import pca_oracle as P
+    t0 = time.perf_counter()
+    lm = O.log1p(O.normalize_total(sample, TARGET_SUM, O.ROW))        # scale/mod.rs:59-89 + transform/mod.rs:8-62
+    gv = O.variance(lm, O.COLUMN)                                      # csr.rs:172-186 (sum, count and sum-of-squares passes)
+    sel = O.select_hvg(gv, hvg)
+    dense = O.densify_selected(lm, np.arange(sample.nrows, dtype=np.uint64), sel)
+    P.pca_fit_transform(dense, min(pcs, len(sel)), True, True)
+    return time.perf_counter() - t0
+
+
 def cpu_baseline(args, sample_cells, repeats=1):
     from oracle import oracle as O
     from singlerust_b200 import synth
@@ -141,7 +156,11 @@ def cpu_baseline(args, sample_cells, repeats=1):
     sample = O.synth_csr(SEED, sample_cells, args.genes, thr, amp)
     times = [cpu_pipeline_once(sample, args.hvg, args.pcs) for _ in range(repeats)]
     t = min(times)
+    t_faithful = cpu_pipeline_reference_faithful(sample, args.hvg, args.pcs)
     return {"value": sample_cells / t, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "reference_faithful": {"value": sample_cells / t_faithful, "unit": UNIT, "cores": 1,
+                                   "note": "serial stats loops and pass structure as in the reference (its rayon pool is only "
+                                           "handed to the SVD); same sample"},
             "sample": f"first {sample_cells} cells of the same synthetic matrix (seed 0x{SEED:X}), full pipeline, "
                       f"{t:.2f} s; stats loops threaded with OpenMP, PCA = LAPACK gesdd via NumPy; the reference's own "
                       f"stats loops are single-threaded (SURVEY F2)"}, times
