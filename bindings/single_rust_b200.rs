@@ -26,7 +26,7 @@ extern "C" {
     pub fn srb_ctx_create(device: i32, out: *mut *mut srb_ctx) -> i32;
     pub fn srb_ctx_destroy(ctx: *mut srb_ctx) -> i32;
     pub fn srb_ctx_set_value_mode(ctx: *mut srb_ctx, mode: i32) -> i32;
-    pub fn srb_ctx_set_upload_mode(ctx: *mut srb_ctx, mode: i32) -> i32;   // 0 device-narrow, 1 host-pack, 2 auto, 3 host-pack + values
+    pub fn srb_ctx_set_upload_mode(ctx: *mut srb_ctx, mode: i32) -> i32;   // 0 device-narrow, 1 host-pack, 2 auto, 3 host-pack + values, 4 host-pack + values while the host is ahead
     pub fn srb_ctx_set_eig_mode(ctx: *mut srb_ctx, mode: i32) -> i32;      // 0 syevd, 1 chfsi
     pub fn srb_ctx_last_eig(ctx: *mut srb_ctx, solver: *mut i32, block_products: *mut i32, outer_iterations: *mut i32,
                             max_residual: *mut f64) -> i32;

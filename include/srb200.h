@@ -65,11 +65,14 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *   HOST_PACK_VALUES  HOST_PACK, and f32 values travel as u8 / u16 for every chunk in which that is lossless (raw
  *                  counts; bit-identical f32 on the device). Pays only when the link, not the host, is the bottleneck:
  *                  on the 16-core bench host it is slower than HOST_PACK (measured, profiles/), so AUTO never picks it
+ *   HOST_PACK_ADAPTIVE  HOST_PACK, and a chunk's values are packed only while the host is ahead of the link (the staging
+ *                  slot's previous DMA is still in flight), so the two stay balanced. Not yet measured (round 2).
  *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
  *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
- * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values) overrides it. */
+ * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values | adaptive) overrides it. */
 typedef enum srb_upload_mode {
-    SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2, SRB_UPLOAD_HOST_PACK_VALUES = 3
+    SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2, SRB_UPLOAD_HOST_PACK_VALUES = 3,
+    SRB_UPLOAD_HOST_PACK_ADAPTIVE = 4
 } srb_upload_mode;
 
 /* K8, the eigensolver behind srb_pca (top-k eigenpairs of the n_sel x n_sel correlation matrix):

@@ -15,7 +15,7 @@ CSR, CSC = 0, 1
 VALUES_COMPACT, VALUES_FAITHFUL = 0, 1
 GRAM_TENSOR, GRAM_FP64 = 0, 1
 EIG_SYEVD, EIG_CHFSI = 0, 1
-UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK, UPLOAD_AUTO, UPLOAD_HOST_PACK_VALUES = 0, 1, 2, 3
+UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK, UPLOAD_AUTO, UPLOAD_HOST_PACK_VALUES, UPLOAD_HOST_PACK_ADAPTIVE = 0, 1, 2, 3, 4
 
 DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
           np.dtype(np.uint8): 4, np.dtype(np.uint16): 5, np.dtype(np.uint32): 6, np.dtype(np.uint64): 7,

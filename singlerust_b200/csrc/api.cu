@@ -231,6 +231,7 @@ static int upload_pack_mode() {
         if (!e) v = SRB_UPLOAD_DEFAULT_MODE;
         else if (!strcmp(e, "auto")) v = SRB_UPLOAD_AUTO;
         else if (!strcmp(e, "values")) v = SRB_UPLOAD_HOST_PACK_VALUES;
+        else if (!strcmp(e, "adaptive")) v = SRB_UPLOAD_HOST_PACK_ADAPTIVE;
         else v = atoi(e) != 0 ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
     }
     return v;
@@ -278,13 +279,13 @@ __global__ void unpack_values_kernel(const uint8_t *__restrict__ pk, float *__re
 // indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too.
 // Returns the bytes that crossed the link.
 static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
-                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val, bool want_value_packing) {
+                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val, int value_packing /* 0 never, 1 always, 2 when the host is ahead of the link */) {
     if (n == 0) return 0;
     cudaStream_t s = c->stream;
     const int pw = bound <= 65536 ? 2 : 4;
     const int nthreads = upload_threads(c);
     const bool stage_vals = values && host_is_pageable(values);
-    const bool pack_vals = values && vsz == 4 && want_value_packing;  // f32 counts -> u8 / u16 where lossless
+    const bool pack_vals = values && vsz == 4 && value_packing != 0;  // f32 counts -> u8 / u16 where lossless
     constexpr int kChunkShift = 22;
     const uint64_t chunk = std::min<uint64_t>(n, 1ull << kChunkShift);
     const uint64_t nchunks = (n + chunk - 1) / chunk;
@@ -303,6 +304,10 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
     for (uint64_t o = 0; o < n; o += chunk, ++ci) {
         const uint64_t len = std::min<uint64_t>(chunk, n - o);
         const int slot = (int)(ci % srb_ctx::kUpSlots);
+        // ADAPTIVE: the slot's previous DMA still running means the host is ahead of the link, so this chunk can afford the
+        // extra host pass that halves its link bytes; when the link is the one waiting, the values go raw
+        bool pack_this = value_packing == 1;
+        if (value_packing == 2 && c->up_ev_used[slot]) pack_this = cudaEventQuery(c->up_ev[slot]) == cudaErrorNotReady;
         if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous DMA is done
         char *h_idx = (char *)c->up_ring + slot_bytes * slot, *h_val = h_idx + idx_bytes;
         oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
@@ -311,7 +316,7 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
         if (values) {
             const char *src = (const char *)values + o * vsz;
             int w = 0;
-            while (vstate) {
+            while (vstate && pack_this) {
                 if (host_pack_values_f32((const float *)src, len, h_val, vstate, nthreads)) {
                     w = vstate;
                     break;
@@ -474,7 +479,7 @@ int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
     SRB_API_BEGIN
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
     SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO ||
-                    mode == SRB_UPLOAD_HOST_PACK_VALUES, SRB_ERR_INVALID_ARG, "bad upload mode");
+                    mode == SRB_UPLOAD_HOST_PACK_VALUES || mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE, SRB_ERR_INVALID_ARG, "bad upload mode");
     ctx->upload_mode = mode;
     SRB_API_END
 }
@@ -540,7 +545,7 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
         upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
     }
     const int up_mode = effective_upload_mode(ctx, nnz);
-    const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES;
+    const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES || up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE;
     if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
     std::unique_ptr<srb_mat> m(new srb_mat());
     m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
@@ -554,7 +559,8 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     uint64_t link_bytes = 0;
     if (packed)
         link_bytes = upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
-                                   direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p, up_mode == SRB_UPLOAD_HOST_PACK_VALUES);
+                                   direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p,
+                                   up_mode == SRB_UPLOAD_HOST_PACK_VALUES ? 1 : up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ? 2 : 0);
     if (!(packed && direct)) {
         if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
         else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());
