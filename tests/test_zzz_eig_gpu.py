@@ -39,8 +39,9 @@ def both_solvers(ffi, ctx, m, sel, k):
 
 def check_same(a, b, k):
     np.testing.assert_allclose(b["explained_variance_ratio"], a["explained_variance_ratio"], rtol=1e-9)
-    np.testing.assert_allclose(sign_align(b["components"], a["components"]), a["components"], atol=1e-7)
-    np.testing.assert_allclose(sign_align(b["scores"], a["scores"]), a["scores"], rtol=1e-6, atol=1e-6 * np.abs(a["scores"]).max())
+    # two converged fp64 solvers agree to ~1e-11 here; the asserted bound is the parity tolerance with a margin of 10
+    np.testing.assert_allclose(sign_align(b["components"], a["components"]), a["components"], atol=1e-6)
+    np.testing.assert_allclose(sign_align(b["scores"], a["scores"]), a["scores"], rtol=0, atol=1e-6 * np.abs(a["scores"]).max())
     V = b["components"]
     np.testing.assert_allclose(V.T @ V, np.eye(k), atol=1e-9)
 
