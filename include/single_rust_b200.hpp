@@ -163,6 +163,18 @@ public:
     Device &operator=(const Device &) = delete;
     srb_ctx *handle() const { return h_; }
     void set_upload_mode(srb_upload_mode m) { detail::check(srb_ctx_set_upload_mode(h_, m)); }
+    void set_eig_mode(srb_eig_mode m) { detail::check(srb_ctx_set_eig_mode(h_, m)); }
+    /// Multi-GPU (new; the reference is single-process): one Device per rank, X sharded by cell-row
+    /// (DeviceMatrix::set_shard). `id` comes from unique_id() on rank 0 and reaches the other ranks through the launcher.
+    struct CommId {
+        unsigned char bytes[128];
+    };
+    static CommId unique_id() {
+        CommId id{};
+        detail::check(srb_comm_unique_id(id.bytes));
+        return id;
+    }
+    void comm_init(const CommId &id, int32_t rank, int32_t nranks) { detail::check(srb_ctx_comm_init(h_, id.bytes, rank, nranks)); }
     void synchronize() { detail::check(srb_ctx_synchronize(h_)); }
 };
 
@@ -216,6 +228,9 @@ public:
         return shared::is_row(d) ? i.nrows : i.ncols;
     }
 
+    /// this rank's rows are [global_row0, global_row0 + nrows) of a matrix of global_nrows cells: per-gene results are
+    /// then allreduced over the ranks of the Device's communicator, per-cell results stay local
+    void set_shard(uint64_t global_row0, uint64_t global_nrows) { detail::check(srb_mat_set_shard(h_, global_row0, global_nrows)); }
     DeviceMatrix clone() const {  // IMAnnData::deep_clone of X: copy-on-write on the device
         srb_mat *h = nullptr;
         detail::check(srb_mat_clone(h_, &h));
