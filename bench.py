@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-inflight", type=int, default=2, help="e2e steps in flight on one GPU (one context + stream + host "
                     "thread each): the upload of step i+1 overlaps the kernels and the score download of step i. N = 1 only")
-    ap.add_argument("--upload-mode", default="default", choices=["default", "device_narrow", "host_pack", "auto", "host_pack_values", "host_pack_adaptive"],
+    ap.add_argument("--upload-mode", default="default", choices=["default", "device_narrow", "host_pack", "auto", "host_pack_values", "host_pack_adaptive", "host_pack_delta"],
                     help="how the e2e leg moves the u64 index array over PCIe (srb_ctx_set_upload_mode); default = library default")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -436,7 +436,8 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
         src.free()
 
     modes = {"device_narrow": _ffi.UPLOAD_DEVICE_NARROW, "host_pack": _ffi.UPLOAD_HOST_PACK, "auto": _ffi.UPLOAD_AUTO,
-             "host_pack_values": _ffi.UPLOAD_HOST_PACK_VALUES, "host_pack_adaptive": _ffi.UPLOAD_HOST_PACK_ADAPTIVE}
+             "host_pack_values": _ffi.UPLOAD_HOST_PACK_VALUES, "host_pack_adaptive": _ffi.UPLOAD_HOST_PACK_ADAPTIVE,
+             "host_pack_delta": _ffi.UPLOAD_HOST_PACK_DELTA}
     # lanes: independent contexts on this GPU; with more than one rank every lane would need its own communicator and a
     # rank-consistent collective order, so pipelining is a single-GPU feature
     L = max(1, args.e2e_inflight) if world == 1 else 1

@@ -19,6 +19,9 @@ extern "C" {
     pub fn srb_version() -> *const c_char;
     pub fn srb_last_error_message() -> *const c_char;
     pub fn srb_kernel_launch_count() -> u64;
+    pub fn srb_host_delta_encode(indices: *const c_void, offsets: *const c_void, idx_width: i32, nmajor: u64, nnz: u64,
+                                 bound: u64, chunk: u64, nthreads: i32, codes: *mut u8, esc_pos: *mut u64,
+                                 esc_val: *mut u32, esc_cap: u64, n_esc: *mut u64, out_of_bounds: *mut i32) -> i32;
     pub fn srb_host_pack_values_f32(src: *const f32, n: u64, dst: *mut c_void, dst_width: i32, nthreads: i32,
                                     lossless: *mut i32) -> i32;
     pub fn srb_host_pack_indices(src: *const c_void, src_width: i32, n: u64, dst: *mut c_void, dst_width: i32,
@@ -26,7 +29,7 @@ extern "C" {
     pub fn srb_ctx_create(device: i32, out: *mut *mut srb_ctx) -> i32;
     pub fn srb_ctx_destroy(ctx: *mut srb_ctx) -> i32;
     pub fn srb_ctx_set_value_mode(ctx: *mut srb_ctx, mode: i32) -> i32;
-    pub fn srb_ctx_set_upload_mode(ctx: *mut srb_ctx, mode: i32) -> i32;   // 0 device-narrow, 1 host-pack, 2 auto, 3 host-pack + values, 4 host-pack + values while the host is ahead
+    pub fn srb_ctx_set_upload_mode(ctx: *mut srb_ctx, mode: i32) -> i32;   // 0 device-narrow, 1 host-pack, 2 auto, 3 host-pack + values, 4 host-pack + values while the host is ahead, 5 host-pack with delta-coded indices
     pub fn srb_ctx_set_eig_mode(ctx: *mut srb_ctx, mode: i32) -> i32;      // 0 syevd, 1 chfsi
     pub fn srb_ctx_last_eig(ctx: *mut srb_ctx, solver: *mut i32, block_products: *mut i32, outer_iterations: *mut i32,
                             max_residual: *mut f64) -> i32;

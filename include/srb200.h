@@ -67,12 +67,15 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *                  on the 16-core bench host it is slower than HOST_PACK (measured, profiles/), so AUTO never picks it
  *   HOST_PACK_ADAPTIVE  HOST_PACK, and a chunk's values are packed only while the host is ahead of the link (the staging
  *                  slot's previous DMA is still in flight), so the two stay balanced. Not yet measured (round 2).
+ *   HOST_PACK_DELTA  HOST_PACK with the sorted indices of each line delta-coded to ONE byte per entry (gap to the previous
+ *                  index; gaps >= 255, line starts beyond 254 and non-canonical pairs escape to a side list), rebuilt
+ *                  exactly on the device. Host coder tested on the CPU; device decode not yet measured (round 2).
  *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
  *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
- * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values | adaptive) overrides it. */
+ * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values | adaptive | delta) overrides it. */
 typedef enum srb_upload_mode {
     SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2, SRB_UPLOAD_HOST_PACK_VALUES = 3,
-    SRB_UPLOAD_HOST_PACK_ADAPTIVE = 4
+    SRB_UPLOAD_HOST_PACK_ADAPTIVE = 4, SRB_UPLOAD_HOST_PACK_DELTA = 5
 } srb_upload_mode;
 
 /* K8, the eigensolver behind srb_pca (top-k eigenpairs of the n_sel x n_sel correlation matrix):
@@ -102,6 +105,14 @@ int32_t srb_host_pack_indices(const void *src, int32_t src_width, uint64_t n, vo
  * [0, 2^(8 dst_width)) whose f32 bit pattern the device can rebuild exactly (else dst is unspecified) */
 int32_t srb_host_pack_values_f32(const float *src, uint64_t n, void *dst, int32_t dst_width, int32_t nthreads,
                                  int32_t *lossless);
+
+/* the delta coder of the HOST_PACK_DELTA upload, for testing (no GPU): codes[i] = indices[i] - previous index of the line
+ * (0 at a line start) when < 255, else 255 with (position, full index) appended to esc_pos / esc_val (capacity esc_cap;
+ * *n_esc = number produced). `chunk` = entries per encoding call, as the upload chunks them. Returns 0, -1 bad argument,
+ * -2 escape capacity too small, -3 offsets not monotone / not ending at nnz. */
+int32_t srb_host_delta_encode(const void *indices, const void *offsets, int32_t idx_width, uint64_t nmajor, uint64_t nnz,
+                              uint64_t bound, uint64_t chunk, int32_t nthreads, uint8_t *codes, uint64_t *esc_pos,
+                              uint32_t *esc_val, uint64_t esc_cap, uint64_t *n_esc, int32_t *out_of_bounds);
 
 /* ---- context ------------------------------------------------------------------------------------ */
 int32_t srb_ctx_create(int32_t device, srb_ctx **out);

@@ -16,6 +16,7 @@ VALUES_COMPACT, VALUES_FAITHFUL = 0, 1
 GRAM_TENSOR, GRAM_FP64 = 0, 1
 EIG_SYEVD, EIG_CHFSI = 0, 1
 UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK, UPLOAD_AUTO, UPLOAD_HOST_PACK_VALUES, UPLOAD_HOST_PACK_ADAPTIVE = 0, 1, 2, 3, 4
+UPLOAD_HOST_PACK_DELTA = 5
 
 DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
           np.dtype(np.uint8): 4, np.dtype(np.uint16): 5, np.dtype(np.uint32): 6, np.dtype(np.uint64): 7,
@@ -59,6 +60,7 @@ def lib() -> C.CDLL:
             "srb_ctx_set_eig_mode": [vp, i32],
             "srb_ctx_last_eig": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f64)],
             "srb_host_pack_values_f32": [vp, u64, vp, i32, i32, C.POINTER(i32)],
+            "srb_host_delta_encode": [vp, vp, i32, u64, u64, u64, u64, i32, vp, vp, vp, u64, C.POINTER(u64), C.POINTER(i32)],
             "srb_ctx_synchronize": [vp],
             "srb_comm_unique_id": [vp],
             "srb_ctx_comm_init": [vp, vp, i32, i32],
@@ -133,6 +135,20 @@ def host_pack_indices(src: np.ndarray, dst_width: int, bound: int, nthreads: int
     if rc != 0:
         raise ValueError("srb_host_pack_indices: bad argument")
     return dst, bool(oob.value)
+
+
+def host_delta_encode(offsets: np.ndarray, indices: np.ndarray, bound: int, chunk: int = 1 << 22, nthreads: int = 0):
+    """Delta coder of the HOST_PACK_DELTA upload (no GPU). Returns (codes u8, escape positions, escape values, oob)."""
+    assert offsets.dtype == indices.dtype and offsets.dtype in (np.uint64, np.uint32)
+    offsets, indices = np.ascontiguousarray(offsets), np.ascontiguousarray(indices)
+    nnz, cap = indices.shape[0], max(1024, indices.shape[0])
+    codes, pos, val = np.empty(nnz, np.uint8), np.empty(cap, np.uint64), np.empty(cap, np.uint32)
+    n, oob = C.c_uint64(0), C.c_int32(0)
+    rc = lib().srb_host_delta_encode(_ptr(indices), _ptr(offsets), indices.dtype.itemsize, offsets.shape[0] - 1, nnz, bound, chunk,
+                                     nthreads, _ptr(codes), _ptr(pos), _ptr(val), cap, C.byref(n), C.byref(oob))
+    if rc != 0:
+        raise ValueError(f"srb_host_delta_encode: {rc}")
+    return codes, pos[:n.value].copy(), val[:n.value].copy(), bool(oob.value)
 
 
 def host_pack_values_f32(src: np.ndarray, dst_width: int, nthreads: int = 0):

@@ -232,6 +232,7 @@ static int upload_pack_mode() {
         else if (!strcmp(e, "auto")) v = SRB_UPLOAD_AUTO;
         else if (!strcmp(e, "values")) v = SRB_UPLOAD_HOST_PACK_VALUES;
         else if (!strcmp(e, "adaptive")) v = SRB_UPLOAD_HOST_PACK_ADAPTIVE;
+        else if (!strcmp(e, "delta")) v = SRB_UPLOAD_HOST_PACK_DELTA;
         else v = atoi(e) != 0 ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
     }
     return v;
@@ -276,13 +277,62 @@ __global__ void unpack_values_kernel(const uint8_t *__restrict__ pk, float *__re
         else if (w == 2) out[i] = (float)reinterpret_cast<const uint16_t *>(pk)[i];
     }
 }
+// HOST_PACK_DELTA: rebuild the u32 indices from the one-byte gap codes (host_pack.cpp). One warp per line: a segmented
+// inclusive scan in which an escape (code 255: the full index sits in the sorted side list) restarts the running sum.
+__global__ void delta_decode_kernel(const uint8_t *__restrict__ code, const int64_t *__restrict__ off, uint64_t nmajor,
+                                    const uint64_t *__restrict__ esc_pos, const uint32_t *__restrict__ esc_val, uint64_t n_esc,
+                                    uint64_t bound, uint32_t *__restrict__ out, uint32_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t bad = 0;
+    for (uint64_t r = warp; r < nmajor; r += nwarps) {
+        const int64_t a = off[r], b = off[r + 1];
+        uint32_t carry = 0;
+        for (int64_t base = a; base < b; base += 32) {
+            const int64_t i = base + lane;
+            const bool valid = i < b;
+            uint32_t v = valid ? code[i] : 0u;
+            int reset = 0;
+            if (valid && v == 255u) {  // binary search of the escape list for position i
+                uint64_t lo = 0, hi = n_esc;
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (esc_pos[mid] < (uint64_t)i) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < n_esc && esc_pos[lo] == (uint64_t)i) v = esc_val[lo];
+                else bad = 1;  // cannot happen for codes produced by host_delta_encode
+                reset = 1;
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t pv = __shfl_up_sync(0xffffffffu, v, o);
+                const int pr = __shfl_up_sync(0xffffffffu, reset, o);
+                if (lane >= o && !reset) v += pv, reset = pr;
+            }
+            const uint32_t col = reset ? v : v + carry;
+            if (valid) {
+                out[i] = col;
+                bad |= (uint32_t)((uint64_t)col >= bound);
+            }
+            carry = __shfl_sync(0xffffffffu, col, 31);
+        }
+    }
+    if (bad) atomicOr(flags, 1u);
+}
+
 // indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too.
 // Returns the bytes that crossed the link.
 static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
-                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val, int value_packing /* 0 never, 1 always, 2 when the host is ahead of the link */) {
+                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val, int value_packing /* 0 never, 1 always, 2 when the host is ahead of the link */,
+                              const void *offsets = nullptr, uint64_t nmajor = 0, const int64_t *d_offsets = nullptr) {
     if (n == 0) return 0;
     cudaStream_t s = c->stream;
-    const int pw = bound <= 65536 ? 2 : 4;
+    // delta coding (one byte per entry) needs trustworthy offsets to walk the lines; otherwise plain narrowing
+    const bool delta = offsets && d_offsets && host_offsets_valid(offsets, width, nmajor, n);
+    const int pw = delta ? 1 : (bound <= 65536 ? 2 : 4);
+    DeltaEscapes esc;
     const int nthreads = upload_threads(c);
     const bool stage_vals = values && host_is_pageable(values);
     const bool pack_vals = values && vsz == 4 && value_packing != 0;  // f32 counts -> u8 / u16 where lossless
@@ -294,9 +344,9 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
     const size_t slot_bytes = idx_bytes + ((val_bytes + 255) & ~size_t(255));
     ensure_upload_ring(c, slot_bytes * srb_ctx::kUpSlots);
     Buf dpk, dvpk;
-    if (pw == 2) dpk = dev_alloc(s, n * 2);
+    if (pw < 4) dpk = dev_alloc(s, n * pw);
     if (pack_vals) dvpk = dev_alloc(s, nchunks * chunk * 2);
-    char *d_pk = pw == 2 ? dpk->as<char>() : (char *)d_idx;
+    char *d_pk = pw < 4 ? dpk->as<char>() : (char *)d_idx;
     std::vector<uint8_t> widths(nchunks, 0);
     int vstate = pack_vals ? 1 : 0;  // 1: try u8, 2: try u16, 0: raw (sticky: a chunk that refuses widens all later ones)
     bool oob = false, any_packed = false;
@@ -310,7 +360,8 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
         if (value_packing == 2 && c->up_ev_used[slot]) pack_this = cudaEventQuery(c->up_ev[slot]) == cudaErrorNotReady;
         if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous DMA is done
         char *h_idx = (char *)c->up_ring + slot_bytes * slot, *h_val = h_idx + idx_bytes;
-        oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
+        if (delta) oob |= host_delta_encode(indices, offsets, width, nmajor, o, len, (uint8_t *)h_idx, bound, nthreads, esc);
+        else oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
         SRB_CUDA(cudaMemcpyAsync(d_pk + o * pw, h_idx, len * pw, cudaMemcpyHostToDevice, s));
         link += len * pw;
         if (values) {
@@ -340,8 +391,22 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
         SRB_CUDA(cudaEventRecord(c->up_ev[slot], s));
         c->up_ev_used[slot] = true;
     }
-    if (pw == 2)
+    bool sync_needed = false;
+    if (delta) {
+        const uint64_t ne = esc.pos.size();
+        Buf dpos = dev_alloc(s, 8 * std::max<uint64_t>(ne, 1)), dval = dev_alloc(s, 4 * std::max<uint64_t>(ne, 1));
+        if (ne) {
+            SRB_CUDA(cudaMemcpyAsync(dpos->p, esc.pos.data(), 8 * ne, cudaMemcpyHostToDevice, s));
+            SRB_CUDA(cudaMemcpyAsync(dval->p, esc.val.data(), 4 * ne, cudaMemcpyHostToDevice, s));
+            link += 12 * ne;
+        }
+        const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nmajor + 7) / 8, (uint64_t)c->sm_count * 16));
+        SRB_LAUNCH(delta_decode_kernel, g, 256, 0, s, dpk->as<uint8_t>(), d_offsets, nmajor, dpos->as<uint64_t>(), dval->as<uint32_t>(), ne, bound, d_idx, d_flags);
+        sync_needed = true;  // `esc` (pageable) and the escape buffers are done with
+    } else if (pw == 2) {
         SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, n), 256, 0, s, dpk->as<uint16_t>(), d_idx, n, bound, d_flags);
+    }
+    if (sync_needed) SRB_CUDA(cudaStreamSynchronize(s));
     if (any_packed) {
         Buf dw = dev_alloc(s, nchunks);
         SRB_CUDA(cudaMemcpyAsync(dw->p, widths.data(), nchunks, cudaMemcpyHostToDevice, s));
@@ -479,7 +544,8 @@ int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
     SRB_API_BEGIN
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
     SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO ||
-                    mode == SRB_UPLOAD_HOST_PACK_VALUES || mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE, SRB_ERR_INVALID_ARG, "bad upload mode");
+                    mode == SRB_UPLOAD_HOST_PACK_VALUES || mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE || mode == SRB_UPLOAD_HOST_PACK_DELTA,
+                SRB_ERR_INVALID_ARG, "bad upload mode");
     ctx->upload_mode = mode;
     SRB_API_END
 }
@@ -545,7 +611,8 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
         upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
     }
     const int up_mode = effective_upload_mode(ctx, nnz);
-    const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES || up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE;
+    const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES || up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ||
+                        up_mode == SRB_UPLOAD_HOST_PACK_DELTA;
     if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
     std::unique_ptr<srb_mat> m(new srb_mat());
     m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
@@ -560,7 +627,8 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     if (packed)
         link_bytes = upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
                                    direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p,
-                                   up_mode == SRB_UPLOAD_HOST_PACK_VALUES ? 1 : up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ? 2 : 0);
+                                   up_mode == SRB_UPLOAD_HOST_PACK_VALUES ? 1 : up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ? 2 : 0,
+                                   up_mode == SRB_UPLOAD_HOST_PACK_DELTA ? offsets : nullptr, nmajor, st->offsets->as<int64_t>());
     if (!(packed && direct)) {
         if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
         else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());

@@ -213,7 +213,126 @@ bool host_pack_values_f32(const float *src, uint64_t n, void *dst, int dst_width
     return all == 0;
 }
 
+// ---- delta coding of the sorted minor indices ------------------------------------------------------------------------
+// Within a line the indices are strictly increasing (nalgebra-sparse invariant), so at 5 % density the gap to the
+// previous index averages 20: one byte per entry instead of two. code = index - previous (previous = 0 at a line start)
+// when that is < 255, else the escape 255 with the full index in a side list (position, value), in entry order. A
+// duplicate (gap 0) is representable; an unsorted pair wraps to a huge gap and becomes an escape, so the device rebuilds
+// EXACTLY the caller's array and its canonical-form check still sees what the caller passed.
+#define SRB_DELTA_LOOP(NAME, SRC)                                                                                        \
+    SRB_ISA_CLONES static uint64_t NAME(const SRC *__restrict__ c, uint8_t *__restrict__ d, uint64_t n, uint64_t bm1,    \
+                                        uint64_t *n_escapes) {                                                          \
+        uint64_t acc = 0, esc = 0;                                                                                      \
+        for (uint64_t j = 0; j < n; ++j) { /* c[j - 1] exists: the run starts at the second entry of its line part */    \
+            const uint64_t cur = (uint64_t)c[j], delta = cur - (uint64_t)c[(int64_t)j - 1];                              \
+            const uint64_t hi = delta >> 8, big = 0 - ((hi | (0 - hi)) >> 63); /* all ones iff delta >= 256 (or wrapped) */ \
+            const uint32_t code = (uint32_t)((delta | big) & 255);                                                      \
+            acc |= cur | (bm1 - cur);                                                                                   \
+            esc += (code + 1) >> 8;                                                                                     \
+            d[j] = (uint8_t)code;                                                                                       \
+        }                                                                                                               \
+        *n_escapes = esc;                                                                                               \
+        return acc;                                                                                                     \
+    }
+SRB_DELTA_LOOP(delta_run_u64, uint64_t)
+SRB_DELTA_LOOP(delta_run_u32, uint32_t)
+
+template <class IDX, class OFF>
+static uint64_t delta_part(const IDX *cols, const OFF *offs, uint64_t nmajor, uint64_t a, uint64_t b, uint8_t *dst, uint64_t o,
+                           uint64_t bm1, DeltaEscapes &esc) {
+    if (a >= b) return 0;
+    // line containing entry a: the last r with offs[r] <= a (empty lines before it are skipped by the search)
+    uint64_t r = (uint64_t)(std::upper_bound(offs, offs + nmajor + 1, (OFF)a) - offs) - 1;
+    uint64_t acc = 0, i = a;
+    while (i < b) {
+        while (r + 1 <= nmajor && (uint64_t)offs[r + 1] <= i) ++r;  // empty lines
+        const uint64_t line_end = std::min<uint64_t>((uint64_t)offs[r + 1], b);
+        // first entry of this line part
+        const uint64_t cur = (uint64_t)cols[i], prev = (i == (uint64_t)offs[r]) ? 0 : (uint64_t)cols[i - 1];
+        const uint64_t delta = cur - prev;
+        acc |= cur | (bm1 - cur);
+        if (delta < 255) {
+            dst[i - o] = (uint8_t)delta;
+        } else {
+            dst[i - o] = 255;
+            esc.pos.push_back(i), esc.val.push_back((uint32_t)cur);
+        }
+        // the rest of the line part, vectorised
+        const uint64_t n = line_end - (i + 1);
+        if (n) {
+            uint64_t ne = 0;
+            if (sizeof(IDX) == 8) acc |= delta_run_u64((const uint64_t *)(const void *)(cols + i + 1), dst + (i + 1 - o), n, bm1, &ne);
+            else acc |= delta_run_u32((const uint32_t *)(const void *)(cols + i + 1), dst + (i + 1 - o), n, bm1, &ne);
+            if (ne)
+                for (uint64_t j = i + 1; j < line_end; ++j)
+                    if (dst[j - o] == 255) esc.pos.push_back(j), esc.val.push_back((uint32_t)cols[j]);
+        }
+        i = line_end;
+    }
+    return acc;
+}
+
+bool host_offsets_valid(const void *offs, int width, uint64_t nmajor, uint64_t nnz) {
+    uint64_t prev = 0;
+    for (uint64_t r = 0; r <= nmajor; ++r) {
+        const uint64_t v = width == 8 ? ((const uint64_t *)offs)[r] : (uint64_t)((const uint32_t *)offs)[r];
+        if (v < prev || v > nnz || (r == 0 && v != 0)) return false;
+        prev = v;
+    }
+    return prev == nnz;
+}
+
+bool host_delta_encode(const void *cols, const void *offs, int width, uint64_t nmajor, uint64_t o, uint64_t len, uint8_t *dst,
+                       uint64_t bound, int nthreads, DeltaEscapes &esc) {
+    if (len == 0) return false;
+    if (bound == 0) return true;
+    if (bound > (1ull << 63)) bound = 1ull << 63;
+    const uint64_t bm1 = bound - 1;
+    if (nthreads <= 0) nthreads = host_pack_threads();
+    const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads, len >> 16));
+    std::vector<DeltaEscapes> pe((size_t)parts);
+    std::vector<uint64_t> acc((size_t)parts, 0);
+    const uint64_t per = ((len + parts - 1) / parts + 63) & ~uint64_t(63);
+    auto one = [&](int p) {
+        const uint64_t a = o + std::min<uint64_t>(len, per * (uint64_t)p), b = std::min<uint64_t>(o + len, a + per);
+        if (width == 8)
+            acc[(size_t)p] = delta_part((const uint64_t *)cols, (const uint64_t *)offs, nmajor, a, b, dst, o, bm1, pe[(size_t)p]);
+        else
+            acc[(size_t)p] = delta_part((const uint32_t *)cols, (const uint32_t *)offs, nmajor, a, b, dst, o, bm1, pe[(size_t)p]);
+    };
+    if (parts == 1) one(0);
+    else pool().run(parts, one);
+    uint64_t all = 0;
+    for (int p = 0; p < parts; ++p) {  // parts are in entry order, so the merged list stays sorted by position
+        all |= acc[(size_t)p];
+        esc.pos.insert(esc.pos.end(), pe[(size_t)p].pos.begin(), pe[(size_t)p].pos.end());
+        esc.val.insert(esc.val.end(), pe[(size_t)p].val.begin(), pe[(size_t)p].val.end());
+    }
+    return (all >> 63) != 0;
+}
+
 }  // namespace srb
+
+// test hook: delta-encode a whole index array in chunks of `chunk` entries (the upload's chunking); the escape arrays
+// hold up to esc_cap entries (more escapes than that: returns -2 with *n_esc = the number needed)
+extern "C" int32_t srb_host_delta_encode(const void *cols, const void *offs, int32_t width, uint64_t nmajor, uint64_t nnz, uint64_t bound,
+                                         uint64_t chunk, int32_t nthreads, uint8_t *codes, uint64_t *esc_pos, uint32_t *esc_val,
+                                         uint64_t esc_cap, uint64_t *n_esc, int32_t *out_of_bounds) {
+    if ((width != 4 && width != 8) || !offs || (nnz && (!cols || !codes)) || chunk == 0) return -1;
+    if (!srb::host_offsets_valid(offs, width, nmajor, nnz)) return -3;
+    srb::DeltaEscapes esc;
+    bool oob = false;
+    for (uint64_t o = 0; o < nnz; o += chunk)
+        oob |= srb::host_delta_encode(cols, offs, width, nmajor, o, std::min<uint64_t>(chunk, nnz - o), codes + o, bound, nthreads, esc);
+    if (n_esc) *n_esc = esc.pos.size();
+    if (out_of_bounds) *out_of_bounds = oob ? 1 : 0;
+    if (esc.pos.size() > esc_cap) return -2;
+    if (!esc.pos.empty()) {
+        memcpy(esc_pos, esc.pos.data(), 8 * esc.pos.size());
+        memcpy(esc_val, esc.val.data(), 4 * esc.val.size());
+    }
+    return 0;
+}
 
 extern "C" int32_t srb_host_pack_values_f32(const float *src, uint64_t n, void *dst, int32_t dst_width, int32_t nthreads,
                                             int32_t *lossless) {

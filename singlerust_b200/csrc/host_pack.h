@@ -1,6 +1,7 @@
 // host_pack.h — host-side packing helpers of the upload path (host_pack.cpp; plain C++, no CUDA).
 #pragma once
 #include <cstdint>
+#include <vector>
 
 namespace srb {
 // threads the upload path uses (SRB_UPLOAD_THREADS, default min(hardware threads, 16))
@@ -11,6 +12,16 @@ bool host_pack_indices(const void *src, int src_width, uint64_t n, void *dst, in
 // dst[i] = (u8 | u16) src[i] when EVERY src[i] is an integer in [0, 2^(8 dst_width)) with the exact f32 bit pattern of
 // that integer (so the device can rebuild the f32 array bit for bit); returns false otherwise (dst is then garbage)
 bool host_pack_values_f32(const float *src, uint64_t n, void *dst, int dst_width, int nthreads);
+// delta coding of the sorted minor indices (one byte per entry + an escape list); see host_pack.cpp
+struct DeltaEscapes {
+    std::vector<uint64_t> pos;  // global entry positions, ascending
+    std::vector<uint32_t> val;  // the full index at that position
+};
+// offsets[0] == 0, monotone, offsets[nmajor] == nnz (the delta coder walks the lines and must not be led astray)
+bool host_offsets_valid(const void *offs, int width, uint64_t nmajor, uint64_t nnz);
+// codes for the entries [o, o + len) into dst[0 .. len), escapes appended to esc; returns true when any index >= bound
+bool host_delta_encode(const void *cols, const void *offs, int width, uint64_t nmajor, uint64_t o, uint64_t len, uint8_t *dst,
+                       uint64_t bound, int nthreads, DeltaEscapes &esc);
 // threaded memcpy (pageable host memory -> pinned staging ring)
 void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads);
 }  // namespace srb

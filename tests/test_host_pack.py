@@ -71,3 +71,90 @@ def test_value_pack_refuses_anything_lossy(bad):
     x = v.copy()
     x[7] = 256.0
     assert _ffi.host_pack_values_f32(x, 1)[1] is False and _ffi.host_pack_values_f32(x, 2)[1] is True
+
+
+# ---- delta coding of the sorted minor indices (HOST_PACK_DELTA) -------------------------------------------------------
+def delta_decode(offsets, codes, esc_pos, esc_val):
+    """Reference decoder (what the device kernel computes): running sum within a line, restarted at every escape."""
+    out = np.zeros(codes.shape[0], np.uint64)
+    esc = dict(zip(esc_pos.tolist(), esc_val.tolist()))
+    for r in range(offsets.shape[0] - 1):
+        prev = 0
+        for i in range(int(offsets[r]), int(offsets[r + 1])):
+            prev = esc[i] if codes[i] == 255 else prev + int(codes[i])
+            out[i] = prev
+    return out
+
+
+def ragged(rng, nrows, ncols, mean_len, empty=()):
+    lens = rng.poisson(mean_len, nrows).clip(0, ncols)
+    lens[list(empty)] = 0
+    offsets = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    indices = np.concatenate([np.sort(rng.choice(ncols, L, replace=False)) for L in lens] + [np.zeros(0, np.int64)]).astype(np.uint64)
+    return offsets, indices
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.uint32])
+@pytest.mark.parametrize("chunk", [1, 7, 64, 1000, 1 << 22])
+@pytest.mark.parametrize("threads", [1, 0])
+def test_delta_round_trip(dtype, chunk, threads):
+    rng = np.random.default_rng(chunk)
+    off, idx = ragged(rng, 300, 30_000, 40, empty=(0, 5, 6, 299))      # gaps of ~750: most entries are escapes
+    off2, idx2 = ragged(rng, 300, 400, 60, empty=(1, 2))               # dense lines: gaps of a few units, no escapes inside
+    for o, i, ncols in ((off, idx, 30_000), (off2, idx2, 400)):
+        codes, pos, val, oob = _ffi.host_delta_encode(o.astype(dtype), i.astype(dtype), ncols, chunk, threads)
+        assert not oob
+        assert np.all(np.diff(pos.astype(np.int64)) > 0)                 # positions ascending
+        assert np.array_equal(np.nonzero(codes == 255)[0], pos)          # one list entry per escape code
+        np.testing.assert_array_equal(delta_decode(o, codes, pos, val), i)
+    assert (codes == 255).sum() <= 300                                   # dense case: at most the line starts escape
+
+
+def test_delta_keeps_non_canonical_input_exact():
+    """Duplicates (gap 0) and unsorted pairs (negative gap -> escape) must decode to exactly what the caller passed, so
+    the device's canonical-form check still reports them."""
+    off = np.array([0, 4, 4, 9], np.uint64)
+    idx = np.array([3, 3, 900, 2, 0, 254, 509, 510, 100], np.uint64)
+    codes, pos, val, oob = _ffi.host_delta_encode(off, idx, 1000, 3)
+    assert not oob
+    assert codes.tolist() == [3, 0, 255, 255, 0, 254, 255, 1, 255]
+    assert pos.tolist() == [2, 3, 6, 8] and val.tolist() == [900, 2, 509, 100]
+    np.testing.assert_array_equal(delta_decode(off, codes, pos, val), idx)
+
+
+def test_delta_bounds_and_bad_offsets():
+    off, idx = ragged(np.random.default_rng(2), 50, 500, 20)
+    assert _ffi.host_delta_encode(off, idx, 500)[3] is False
+    bad = idx.copy()
+    bad[17] = 500
+    assert _ffi.host_delta_encode(off, bad, 500)[3] is True
+    bad[17] = (1 << 63) + 4
+    assert _ffi.host_delta_encode(off, bad, 500)[3] is True
+    wrong = off.copy()
+    wrong[10], wrong[11] = wrong[11], wrong[10] + 0 if wrong[11] != wrong[10] else wrong[10] + 1
+    if np.any(np.diff(wrong.astype(np.int64)) < 0):
+        with pytest.raises(ValueError, match="-3"):
+            _ffi.host_delta_encode(wrong, idx, 500)
+    short = off.copy()
+    short[-1] -= 1
+    with pytest.raises(ValueError, match="-3"):
+        _ffi.host_delta_encode(short, idx, 500)
+
+
+def test_delta_large_multithreaded_matches_single_thread():
+    rng = np.random.default_rng(9)
+    off, idx = ragged(rng, 4000, 30_000, 1500)                           # 6 M entries, the bench's line length
+    a = _ffi.host_delta_encode(off, idx, 30_000, 1 << 22, 1)
+    b = _ffi.host_delta_encode(off, idx, 30_000, 1 << 20, 0)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert (a[0] == 255).mean() < 1e-3                                   # escapes are rare at 5 % density
+    # spot-check the decode on a slice of lines
+    sub = slice(int(off[100]), int(off[140]))
+    esc = dict(zip(a[1].tolist(), a[2].tolist()))
+    for r in range(100, 140):
+        prev = 0
+        for i in range(int(off[r]), int(off[r + 1])):
+            prev = esc[i] if a[0][i] == 255 else prev + int(a[0][i])
+            assert prev == idx[i]
+    assert sub.stop > sub.start

@@ -39,7 +39,7 @@ emit({"what": "setup", "nnz": nnz, "pin_and_download_s": time.time() - t0, "thre
 stream = torch.cuda.ExternalStream(ctx.stream)
 ref_sum = None
 for mode, name in ((_ffi.UPLOAD_DEVICE_NARROW, "device_narrow"), (_ffi.UPLOAD_HOST_PACK, "host_pack"),
-                   (_ffi.UPLOAD_HOST_PACK_VALUES, "host_pack_values"), (_ffi.UPLOAD_HOST_PACK_ADAPTIVE, "host_pack_adaptive"),
+                   (_ffi.UPLOAD_HOST_PACK_VALUES, "host_pack_values"), (_ffi.UPLOAD_HOST_PACK_ADAPTIVE, "host_pack_adaptive"), (_ffi.UPLOAD_HOST_PACK_DELTA, "host_pack_delta"),
                    (_ffi.UPLOAD_DEVICE_NARROW, "device_narrow"),
                    (_ffi.UPLOAD_HOST_PACK, "host_pack")):
     ctx.set_upload_mode(mode)
