@@ -158,3 +158,46 @@ def test_delta_large_multithreaded_matches_single_thread():
             prev = esc[i] if a[0][i] == 255 else prev + int(a[0][i])
             assert prev == idx[i]
     assert sub.stop > sub.start
+
+
+def warp_decode_emulation(offsets, codes, esc_pos, esc_val):
+    """Lane-by-lane emulation of api.cu: delta_decode_kernel (32-lane segmented inclusive scan with __shfl_up, an escape
+    restarts the running sum, the last lane's result carries into the next 32 entries of the line)."""
+    out = np.zeros(codes.shape[0], np.uint64)
+    esc = dict(zip(esc_pos.tolist(), esc_val.tolist()))
+    for r in range(offsets.shape[0] - 1):
+        a, b, carry = int(offsets[r]), int(offsets[r + 1]), 0
+        for base in range(a, b, 32):
+            v, reset = [0] * 32, [0] * 32
+            for lane in range(32):
+                i = base + lane
+                if i < b:
+                    v[lane] = int(codes[i])
+                    if v[lane] == 255:
+                        v[lane], reset[lane] = esc[i], 1
+            o = 1
+            while o < 32:
+                pv, pr = v[:], reset[:]                      # __shfl_up_sync reads the values before this step
+                for lane in range(32):
+                    if lane >= o and not reset[lane]:
+                        v[lane] += pv[lane - o]
+                        reset[lane] = pr[lane - o]
+                o <<= 1
+            col = [v[lane] if reset[lane] else v[lane] + carry for lane in range(32)]
+            for lane in range(32):
+                if base + lane < b:
+                    out[base + lane] = col[lane]
+            carry = col[31]
+    return out
+
+
+def test_device_decode_algorithm_by_emulation():
+    rng = np.random.default_rng(4)
+    for ncols, mean_len in ((30_000, 45), (400, 70), (30_000, 1)):
+        off, idx = ragged(rng, 120, ncols, mean_len, empty=(0, 3, 119))
+        codes, pos, val, _ = _ffi.host_delta_encode(off, idx, ncols, 50)
+        np.testing.assert_array_equal(warp_decode_emulation(off, codes, pos, val), idx)
+    off = np.array([0, 4, 4, 9, 75], np.uint64)                        # non-canonical pairs + a line longer than two warps
+    idx = np.concatenate([[3, 3, 900, 2, 0, 254, 509, 510, 100], np.arange(66) * 7]).astype(np.uint64)
+    codes, pos, val, _ = _ffi.host_delta_encode(off, idx, 1000, 5)
+    np.testing.assert_array_equal(warp_decode_emulation(off, codes, pos, val), idx)
