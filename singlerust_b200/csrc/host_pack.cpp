@@ -11,12 +11,15 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <pthread.h>
 #include <thread>
 #include <vector>
 
 #include "host_pack.h"
 
 namespace srb {
+
+static std::atomic<bool> g_forked_child{false};  // set in a forked child: the pool's worker threads do not exist there
 
 // ---- a persistent pool: run(n, fn) calls fn(part) for part in [0, n), part 0 on the calling thread ------------
 class HostPool {
@@ -62,7 +65,7 @@ public:
 
     void run(int parts, const std::function<void(int)> &fn) {
         if (parts <= 0) return;
-        if (parts == 1 || workers_.empty()) {
+        if (parts == 1 || workers_.empty() || g_forked_child.load()) {
             for (int p = 0; p < parts; ++p) fn(p);
             return;
         }
@@ -93,9 +96,16 @@ int host_pack_threads() {
     return n;
 }
 
+// A forked child inherits the pool object but not its worker threads: it must not wait for them.
+static void mark_forked_child() { g_forked_child.store(true); }
+
 static HostPool &pool() {
-    static HostPool p(host_pack_threads() - 1);
-    return p;
+    // leaked on purpose: no static destructor has to join worker threads at process exit (or in a forked child)
+    static HostPool *p = [] {
+        pthread_atfork(nullptr, nullptr, mark_forked_child);
+        return new HostPool(host_pack_threads() - 1);
+    }();
+    return *p;
 }
 
 // ---- the packing loops; cloned per ISA so the .so stays loadable on any x86-64 host -----------------------------

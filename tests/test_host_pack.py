@@ -201,3 +201,29 @@ def test_device_decode_algorithm_by_emulation():
     idx = np.concatenate([[3, 3, 900, 2, 0, 254, 509, 510, 100], np.arange(66) * 7]).astype(np.uint64)
     codes, pos, val, _ = _ffi.host_delta_encode(off, idx, 1000, 5)
     np.testing.assert_array_equal(warp_decode_emulation(off, codes, pos, val), idx)
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")   # forking a multi-threaded process is the scenario under test
+def test_pool_survives_fork():
+    """A forked child has the pool object but none of its worker threads: packing there must run serially, not hang."""
+    import os
+    src = np.random.default_rng(0).integers(0, 30_000, size=3_000_000).astype(np.uint64)
+    _ffi.host_pack_indices(src, 2, 30_000)            # creates the pool in the parent
+    pid = os.fork()
+    if pid == 0:
+        try:
+            d, oob = _ffi.host_pack_indices(src, 2, 30_000)
+            ok = (not oob) and np.array_equal(d, src.astype(np.uint16))
+        except BaseException:
+            ok = False
+        os._exit(0 if ok else 1)
+    for _ in range(600):
+        done, status = os.waitpid(pid, os.WNOHANG)
+        if done:
+            break
+        import time
+        time.sleep(0.05)
+    else:
+        os.kill(pid, 9)
+        pytest.fail("the forked child hung in the packing pool")
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
