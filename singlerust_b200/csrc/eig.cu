@@ -180,7 +180,7 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         const char *e = getenv("SRB_CHFSI_TARGET");
         return std::pow(10.0, e ? std::max(6.0, std::min(14.0, atof(e))) : 11.0);
     }();
-    constexpr int kMaxOuter = 6, kMaxRounds = 24, kMaxDegree = 32;
+    constexpr int kMaxOuter = 6, kMaxRounds = 24, kMaxDegree = 32, kMaxProducts = 400;
     constexpr double kAmpCap = 1e8, kTol = 1e-11;
     uint32_t b = std::min<uint32_t>(d / 4, ((std::max<uint32_t>(3 * k, k + 96) + 63) / 64) * 64);
     if (b_env >= k + 16 && b_env <= d / 2) b = b_env;
@@ -283,6 +283,8 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         int rounds = (int)std::ceil(std::log(kTarget) / std::log(std::max(amp, 1.0001)));
         rounds = std::max(1, std::min(rounds, outer == 0 ? 3 : kMaxRounds));
         if (n_info + 2 * rounds + 1 > 60) return false;
+        // work budget: beyond ~400 block products the iteration would cost more than the syevd it replaces
+        if (st.block_products + rounds * m > kMaxProducts) return false;
         SRB_LAUNCH(shift_copy_kernel, (unsigned)((dd + 255) / 256), 256, 0, es, d_C, Cs, d, c);
         for (int r = 0; r < rounds; ++r) {
             // scaled Chebyshev recurrence (Zhou & Saad): Y_1 = (s1/e) Cs Y_0 ; Y_{i+1} = (2 s_{i+1}/e) Cs Y_i - s_i s_{i+1} Y_{i-1}

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-AMP_CAP, MAX_DEGREE, MAX_ROUNDS, MAX_OUTER = 1e8, 32, 24, 6
+AMP_CAP, MAX_DEGREE, MAX_ROUNDS, MAX_OUTER, MAX_PRODUCTS = 1e8, 32, 24, 6, 400
 
 
 def cheb_filter(mul, Y, m, lo, cut, up):
@@ -87,6 +87,8 @@ def chfsi_topk(C, k, seed=0, L=40, target=1e11, tol=1e-11, b=None, log=None):
         amp = np.cosh(m * np.arccosh(xk))
         R = int(np.ceil(np.log(target) / np.log(max(amp, 1.0001))))
         R = max(1, min(R, 3 if outer == 0 else MAX_ROUNDS))
+        if stats["block_products"] + R * m > MAX_PRODUCTS:
+            return None  # work budget: costlier than the syevd it replaces
         for _ in range(R):
             Y = cheb_filter(lambda X: C @ X, Y, m, lo, cut, up)
             stats["block_products"] += m
