@@ -227,3 +227,33 @@ def test_pool_survives_fork():
         os.kill(pid, 9)
         pytest.fail("the forked child hung in the packing pool")
     assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
+def test_delta_fuzz_against_both_decoders():
+    """Random small matrices, including non-canonical ones, through encode -> reference decode and -> warp emulation."""
+    from hypothesis import given, settings, strategies as st
+
+    @st.composite
+    def lines(draw):
+        nlines = draw(st.integers(1, 6))
+        ncols = draw(st.sampled_from([3, 40, 300, 70_000]))
+        off, idx = [0], []
+        for _ in range(nlines):
+            n = draw(st.integers(0, 70))
+            row = draw(st.lists(st.integers(0, ncols - 1), min_size=n, max_size=n))
+            if draw(st.booleans()):
+                row = sorted(set(row))                                  # canonical line; otherwise anything goes
+            idx += row
+            off.append(len(idx))
+        return np.array(off, np.uint64), np.array(idx, np.uint64), ncols, draw(st.sampled_from([1, 3, 32, 33, 4096]))
+
+    @settings(max_examples=150, deadline=None)
+    @given(lines())
+    def run(case):
+        off, idx, ncols, chunk = case
+        codes, pos, val, oob = _ffi.host_delta_encode(off, idx, ncols, chunk)
+        assert not oob
+        np.testing.assert_array_equal(delta_decode(off, codes, pos, val), idx)
+        np.testing.assert_array_equal(warp_decode_emulation(off, codes, pos, val), idx)
+
+    run()
