@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsrb200.so")
-SOURCES = ["api.cu", "major_stats.cu", "minor_moments.cu", "select.cu", "pca.cu", "gram_tc.cu", "gram_tc2.cu", "eig.cu", "comm.cu",
+SOURCES = ["api.cu", "upload.cu", "major_stats.cu", "minor_moments.cu", "select.cu", "pca.cu", "gram_tc.cu", "gram_tc2.cu", "eig.cu", "comm.cu",
            "synth.cu", "stream.cu", "convert.cu", "subset.cu"]
 HOST_SOURCES = ["host_pack.cpp"]  # plain C++ (g++): host-side marshalling of the upload path, no CUDA
 CXX = os.environ.get("CXX", "/usr/bin/g++")

@@ -233,6 +233,18 @@ void allreduce_f64_max(srb_ctx *ctx, double *d_buf, size_t n);
 void comm_destroy(srb_ctx *ctx);
 void eig_destroy(srb_ctx *ctx);
 
+// element-wise dtype conversion (upload.cu: host dtype -> device storage; api.cu: device storage -> download dtype)
+template <typename SRC, typename DST>
+__global__ void convert_kernel(const SRC *__restrict__ src, DST *__restrict__ dst, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = (DST)src[i];
+}
+// grid of 256-thread blocks for a grid-stride loop over n elements, capped at 16 blocks per SM
+static inline unsigned grid_for(const srb_ctx *c, uint64_t n) {
+    const uint64_t blocks = (n + 255) / 256, cap = (uint64_t)c->sm_count * 16;
+    return (unsigned)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
 // misc device helpers
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

@@ -1,0 +1,394 @@
+// upload.cu — the host -> HBM path of libsrb200: srb_mat_upload (include/srb200.h) and everything behind it. The
+// reference hands over nalgebra-sparse slices (`usize` offsets / indices, values of any DynCsrMatrix dtype;
+// src/shared/statistics/helper/csr.rs:24,32,96); the device copy is int64 offsets, uint32 indices and f32 / f64 values,
+// bounds- and canonical-form-checked. Because PCIe, not the GPU, bounds an end-to-end step, the index array can be packed
+// on the host before it crosses the link (host_pack.cpp) — see the srb_upload_mode comment in the header.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "host_pack.h"
+
+// built-in default of SRB_UPLOAD_PACK (kept in step with _ffi.UPLOAD_DEFAULT)
+#define SRB_UPLOAD_DEFAULT_MODE SRB_UPLOAD_AUTO
+
+namespace srb {
+
+// ---- conversion kernels ------------------------------------------------------------------------------
+// narrow + bounds check; flags[0] |= 1 on out-of-range
+template <typename SRC>
+__global__ void narrow_index_kernel(const SRC *__restrict__ src, uint32_t *__restrict__ dst, uint64_t n, uint64_t bound,
+                                    uint32_t *__restrict__ flags) {
+    uint32_t bad = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = (uint64_t)src[i];
+        bad |= (uint32_t)(v >= bound);
+        dst[i] = (uint32_t)v;
+    }
+    if (bad) atomicOr(flags, 1u);
+}
+// canonical form check: offsets monotone, indices strictly increasing within a line. flags[1] |= 1 otherwise
+__global__ void canonical_check_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx, uint64_t nmajor,
+                                       uint64_t nnz, uint32_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t bad = 0;
+    for (uint64_t r = warp; r < nmajor; r += nwarps) {
+        const int64_t a = off[r], b = off[r + 1];
+        if (a > b || a < 0 || (uint64_t)b > nnz) { bad = 1; continue; }
+        for (int64_t k = a + 1 + lane; k < b; k += 32) bad |= (uint32_t)(idx[k] <= idx[k - 1]);
+    }
+    if (bad) atomicOr(flags + 1, 1u);
+}
+
+// host array (any supported dtype) -> device array of DST, through a bounded staging buffer
+template <typename DST>
+static void upload_convert(srb_ctx *c, const void *host, int dtype, uint64_t n, DST *d_dst) {
+    if (n == 0) return;
+    cudaStream_t s = c->stream;
+    size_t esz;
+    switch (dtype) {
+        case SRB_I8: case SRB_U8: esz = 1; break;
+        case SRB_I16: case SRB_U16: esz = 2; break;
+        case SRB_I32: case SRB_U32: case SRB_F32: esz = 4; break;
+        case SRB_F64: esz = 8; break;
+        default: throw Error(SRB_ERR_UNSUPPORTED_DTYPE, "dtype not supported (the reference panics for I64/U64/Usize/Bool/String)");
+    }
+    if ((dtype == SRB_F32 && sizeof(DST) == 4) || (dtype == SRB_F64 && sizeof(DST) == 8)) {
+        SRB_CUDA(cudaMemcpyAsync(d_dst, host, n * esz, cudaMemcpyHostToDevice, s));
+        return;
+    }
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 26);
+    Buf stage = dev_alloc(s, chunk * esz);
+    for (uint64_t o = 0; o < n; o += chunk) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - o);
+        SRB_CUDA(cudaMemcpyAsync(stage->p, (const char *)host + o * esz, len * esz, cudaMemcpyHostToDevice, s));
+        const unsigned g = grid_for(c, len);
+        switch (dtype) {
+            case SRB_I8: SRB_LAUNCH((convert_kernel<int8_t, DST>), g, 256, 0, s, stage->as<int8_t>(), d_dst + o, len); break;
+            case SRB_U8: SRB_LAUNCH((convert_kernel<uint8_t, DST>), g, 256, 0, s, stage->as<uint8_t>(), d_dst + o, len); break;
+            case SRB_I16: SRB_LAUNCH((convert_kernel<int16_t, DST>), g, 256, 0, s, stage->as<int16_t>(), d_dst + o, len); break;
+            case SRB_U16: SRB_LAUNCH((convert_kernel<uint16_t, DST>), g, 256, 0, s, stage->as<uint16_t>(), d_dst + o, len); break;
+            case SRB_I32: SRB_LAUNCH((convert_kernel<int32_t, DST>), g, 256, 0, s, stage->as<int32_t>(), d_dst + o, len); break;
+            case SRB_U32: SRB_LAUNCH((convert_kernel<uint32_t, DST>), g, 256, 0, s, stage->as<uint32_t>(), d_dst + o, len); break;
+            case SRB_F32: SRB_LAUNCH((convert_kernel<float, DST>), g, 256, 0, s, stage->as<float>(), d_dst + o, len); break;
+            case SRB_F64: SRB_LAUNCH((convert_kernel<double, DST>), g, 256, 0, s, stage->as<double>(), d_dst + o, len); break;
+        }
+    }
+}
+
+static void upload_indices(srb_ctx *c, const void *host, int width, uint64_t n, uint64_t bound, uint32_t *d_dst,
+                           uint32_t *d_flags) {
+    if (n == 0) return;
+    cudaStream_t s = c->stream;
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 26);
+    Buf stage = dev_alloc(s, chunk * (size_t)width);
+    for (uint64_t o = 0; o < n; o += chunk) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - o);
+        SRB_CUDA(cudaMemcpyAsync(stage->p, (const char *)host + o * width, len * width, cudaMemcpyHostToDevice, s));
+        if (width == 8)
+            SRB_LAUNCH((narrow_index_kernel<uint64_t>), grid_for(c, len), 256, 0, s, stage->as<uint64_t>(), d_dst + o, len, bound, d_flags);
+        else
+            SRB_LAUNCH((narrow_index_kernel<uint32_t>), grid_for(c, len), 256, 0, s, stage->as<uint32_t>(), d_dst + o, len, bound, d_flags);
+    }
+}
+
+// ---- packed upload ------------------------------------------------------------------------------------
+// The reference's col_indices are `usize` (8 bytes); at the bench size they are 12 of the 18 GB one step moves over
+// PCIe. SRB_UPLOAD_PACK=1 narrows them on the HOST (host_pack.cpp, a small thread pool) into a pinned staging ring —
+// 2 bytes per entry when nminor <= 65 536, else 4 — so only 2-4 bytes per entry cross the link; packing chunk c+1
+// overlaps the DMA of chunk c, and the value chunks are enqueued in between so the link never waits for the host.
+// Pageable caller memory (a Rust Vec) is staged through the same ring with a threaded memcpy instead of the
+// driver's single-threaded bounce buffer. The device widens to u32 and repeats the bounds check.
+static int upload_pack_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SRB_UPLOAD_PACK");
+        if (!e) v = SRB_UPLOAD_DEFAULT_MODE;
+        else if (!strcmp(e, "auto")) v = SRB_UPLOAD_AUTO;
+        else if (!strcmp(e, "values")) v = SRB_UPLOAD_HOST_PACK_VALUES;
+        else if (!strcmp(e, "adaptive")) v = SRB_UPLOAD_HOST_PACK_ADAPTIVE;
+        else if (!strcmp(e, "delta")) v = SRB_UPLOAD_HOST_PACK_DELTA;
+        else v = atoi(e) != 0 ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
+    }
+    return v;
+}
+// host threads one context may use for packing: the ranks of a node share its cores
+static int upload_threads(const srb_ctx *c) { return std::max(1, host_pack_threads() / std::max(1, c->nranks)); }
+// AUTO: packing pays when the host narrows faster than the link moves the unpacked array (12 B per entry at ~55 GB/s =
+// 4.6 G entries/s; one host thread packs ~0.9 G entries/s), i.e. with >= 6 threads, and only for arrays worth a ring
+static int effective_upload_mode(const srb_ctx *c, uint64_t nnz) {
+    const int mode = c->upload_mode >= 0 ? c->upload_mode : upload_pack_mode();
+    if (mode == SRB_UPLOAD_AUTO) return (nnz >= (1ull << 20) && upload_threads(c) >= 6) ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
+    return mode;
+}
+static bool host_is_pageable(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+static void ensure_upload_ring(srb_ctx *c, size_t bytes) {
+    if (c->up_ring_bytes >= bytes) return;
+    if (c->up_ring) {
+        SRB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFreeHost(c->up_ring);
+        c->up_ring = nullptr, c->up_ring_bytes = 0;
+    }
+    SRB_CUDA(cudaHostAlloc(&c->up_ring, bytes, cudaHostAllocDefault));
+    c->up_ring_bytes = bytes;
+    for (int i = 0; i < srb_ctx::kUpSlots; ++i)
+        if (!c->up_ev[i]) SRB_CUDA(cudaEventCreateWithFlags(&c->up_ev[i], cudaEventDisableTiming));
+}
+// f32 chunk values that travelled as u8 / u16 (widths[chunk] = 1 | 2; 0 = the chunk was copied raw): rebuild the f32 array.
+// Packed chunk c sits at byte offset 2 * c * chunk of `pk`.
+__global__ void unpack_values_kernel(const uint8_t *__restrict__ pk, float *__restrict__ out, uint64_t n, int chunk_shift,
+                                     const uint8_t *__restrict__ widths) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = i >> chunk_shift, base = c << chunk_shift;  // a single chunk (n < 2^shift) has c = 0
+        const uint8_t w = widths[c];
+        if (w == 1) out[i] = (float)pk[2 * base + (i - base)];
+        else if (w == 2) out[i] = (float)reinterpret_cast<const uint16_t *>(pk)[i];
+    }
+}
+// HOST_PACK_DELTA: rebuild the u32 indices from the one-byte gap codes (host_pack.cpp). One warp per line: a segmented
+// inclusive scan in which an escape (code 255: the full index sits in the sorted side list) restarts the running sum.
+__global__ void delta_decode_kernel(const uint8_t *__restrict__ code, const int64_t *__restrict__ off, uint64_t nmajor,
+                                    const uint64_t *__restrict__ esc_pos, const uint32_t *__restrict__ esc_val, uint64_t n_esc,
+                                    uint64_t bound, uint32_t *__restrict__ out, uint32_t *__restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    uint32_t bad = 0;
+    for (uint64_t r = warp; r < nmajor; r += nwarps) {
+        const int64_t a = off[r], b = off[r + 1];
+        uint32_t carry = 0;
+        for (int64_t base = a; base < b; base += 32) {
+            const int64_t i = base + lane;
+            const bool valid = i < b;
+            uint32_t v = valid ? code[i] : 0u;
+            int reset = 0;
+            if (valid && v == 255u) {  // binary search of the escape list for position i
+                uint64_t lo = 0, hi = n_esc;
+                while (lo < hi) {
+                    const uint64_t mid = (lo + hi) >> 1;
+                    if (esc_pos[mid] < (uint64_t)i) lo = mid + 1;
+                    else hi = mid;
+                }
+                if (lo < n_esc && esc_pos[lo] == (uint64_t)i) v = esc_val[lo];
+                else bad = 1;  // cannot happen for codes produced by host_delta_encode
+                reset = 1;
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t pv = __shfl_up_sync(0xffffffffu, v, o);
+                const int pr = __shfl_up_sync(0xffffffffu, reset, o);
+                if (lane >= o && !reset) v += pv, reset = pr;
+            }
+            const uint32_t col = reset ? v : v + carry;
+            if (valid) {
+                out[i] = col;
+                bad |= (uint32_t)((uint64_t)col >= bound);
+            }
+            carry = __shfl_sync(0xffffffffu, col, 31);
+        }
+    }
+    if (bad) atomicOr(flags, 1u);
+}
+
+// indices (always) and, when `values` is a bit-copy of the device storage (vsz bytes per entry), the values too.
+// Returns the bytes that crossed the link.
+static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx,
+                              uint32_t *d_flags, const void *values, size_t vsz, void *d_val, int value_packing /* 0 never, 1 always, 2 when the host is ahead of the link */,
+                              const void *offsets = nullptr, uint64_t nmajor = 0, const int64_t *d_offsets = nullptr) {
+    if (n == 0) return 0;
+    cudaStream_t s = c->stream;
+    // delta coding (one byte per entry) needs trustworthy offsets to walk the lines; otherwise plain narrowing
+    const bool delta = offsets && d_offsets && host_offsets_valid(offsets, width, nmajor, n);
+    const int pw = delta ? 1 : (bound <= 65536 ? 2 : 4);
+    DeltaEscapes esc;
+    const int nthreads = upload_threads(c);
+    const bool stage_vals = values && host_is_pageable(values);
+    const bool pack_vals = values && vsz == 4 && value_packing != 0;  // f32 counts -> u8 / u16 where lossless
+    constexpr int kChunkShift = 22;
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << kChunkShift);
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    const size_t idx_bytes = (chunk * pw + 255) & ~size_t(255);
+    const size_t val_bytes = stage_vals ? chunk * vsz : (pack_vals ? chunk * 2 : 0);
+    const size_t slot_bytes = idx_bytes + ((val_bytes + 255) & ~size_t(255));
+    ensure_upload_ring(c, slot_bytes * srb_ctx::kUpSlots);
+    Buf dpk, dvpk;
+    if (pw < 4) dpk = dev_alloc(s, n * pw);
+    if (pack_vals) dvpk = dev_alloc(s, nchunks * chunk * 2);
+    char *d_pk = pw < 4 ? dpk->as<char>() : (char *)d_idx;
+    std::vector<uint8_t> widths(nchunks, 0);
+    int vstate = pack_vals ? 1 : 0;  // 1: try u8, 2: try u16, 0: raw (sticky: a chunk that refuses widens all later ones)
+    bool oob = false, any_packed = false;
+    uint64_t ci = 0, link = 0;
+    for (uint64_t o = 0; o < n; o += chunk, ++ci) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - o);
+        const int slot = (int)(ci % srb_ctx::kUpSlots);
+        // ADAPTIVE: the slot's previous DMA still running means the host is ahead of the link, so this chunk can afford the
+        // extra host pass that halves its link bytes; when the link is the one waiting, the values go raw
+        bool pack_this = value_packing == 1;
+        if (value_packing == 2 && c->up_ev_used[slot]) pack_this = cudaEventQuery(c->up_ev[slot]) == cudaErrorNotReady;
+        if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous DMA is done
+        char *h_idx = (char *)c->up_ring + slot_bytes * slot, *h_val = h_idx + idx_bytes;
+        if (delta) oob |= host_delta_encode(indices, offsets, width, nmajor, o, len, (uint8_t *)h_idx, bound, nthreads, esc);
+        else oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
+        SRB_CUDA(cudaMemcpyAsync(d_pk + o * pw, h_idx, len * pw, cudaMemcpyHostToDevice, s));
+        link += len * pw;
+        if (values) {
+            const char *src = (const char *)values + o * vsz;
+            int w = 0;
+            while (vstate && pack_this) {
+                if (host_pack_values_f32((const float *)src, len, h_val, vstate, nthreads)) {
+                    w = vstate;
+                    break;
+                }
+                vstate = vstate == 1 ? 2 : 0;
+            }
+            widths[ci] = (uint8_t)w;
+            if (w) {
+                SRB_CUDA(cudaMemcpyAsync(dvpk->as<char>() + 2 * o, h_val, len * w, cudaMemcpyHostToDevice, s));
+                link += len * w;
+                any_packed = true;
+            } else {
+                if (stage_vals) {
+                    host_copy_parallel(src, h_val, len * vsz, nthreads);
+                    src = h_val;
+                }
+                SRB_CUDA(cudaMemcpyAsync((char *)d_val + o * vsz, src, len * vsz, cudaMemcpyHostToDevice, s));
+                link += len * vsz;
+            }
+        }
+        SRB_CUDA(cudaEventRecord(c->up_ev[slot], s));
+        c->up_ev_used[slot] = true;
+    }
+    bool sync_needed = false;
+    if (delta) {
+        const uint64_t ne = esc.pos.size();
+        Buf dpos = dev_alloc(s, 8 * std::max<uint64_t>(ne, 1)), dval = dev_alloc(s, 4 * std::max<uint64_t>(ne, 1));
+        if (ne) {
+            SRB_CUDA(cudaMemcpyAsync(dpos->p, esc.pos.data(), 8 * ne, cudaMemcpyHostToDevice, s));
+            SRB_CUDA(cudaMemcpyAsync(dval->p, esc.val.data(), 4 * ne, cudaMemcpyHostToDevice, s));
+            link += 12 * ne;
+        }
+        const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nmajor + 7) / 8, (uint64_t)c->sm_count * 16));
+        SRB_LAUNCH(delta_decode_kernel, g, 256, 0, s, dpk->as<uint8_t>(), d_offsets, nmajor, dpos->as<uint64_t>(), dval->as<uint32_t>(), ne, bound, d_idx, d_flags);
+        sync_needed = true;  // `esc` (pageable) and the escape buffers are done with
+    } else if (pw == 2) {
+        SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, n), 256, 0, s, dpk->as<uint16_t>(), d_idx, n, bound, d_flags);
+    }
+    if (sync_needed) SRB_CUDA(cudaStreamSynchronize(s));
+    if (any_packed) {
+        Buf dw = dev_alloc(s, nchunks);
+        SRB_CUDA(cudaMemcpyAsync(dw->p, widths.data(), nchunks, cudaMemcpyHostToDevice, s));
+        SRB_LAUNCH(unpack_values_kernel, grid_for(c, n), 256, 0, s, dvpk->as<uint8_t>(), (float *)d_val, n, kChunkShift, dw->as<uint8_t>());
+        SRB_CUDA(cudaStreamSynchronize(s));  // `widths` (pageable) and the staging ring are done with
+    }
+    if (oob) {
+        SRB_CUDA(cudaStreamSynchronize(s));
+        throw Error(SRB_ERR_INDEX_OOB, "minor index out of bounds");
+    }
+    return link;
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" {
+
+int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO ||
+                    mode == SRB_UPLOAD_HOST_PACK_VALUES || mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE || mode == SRB_UPLOAD_HOST_PACK_DELTA,
+                SRB_ERR_INVALID_ARG, "bad upload mode");
+    ctx->upload_mode = mode;
+    SRB_API_END
+}
+
+int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_packed) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    if (h2d_bytes) *h2d_bytes = ctx->last_upload_h2d;
+    if (host_packed) *host_packed = ctx->last_upload_packed;
+    SRB_API_END
+}
+
+int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t ncols, uint64_t nnz, const void *offsets,
+                       const void *indices, int32_t idx_width, const void *values, int32_t dtype, srb_mat **out) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx && out, SRB_ERR_INVALID_ARG, "null ctx/out");
+    SRB_REQUIRE(format == SRB_CSR || format == SRB_CSC, SRB_ERR_INVALID_ARG, "format must be CSR or CSC");
+    SRB_REQUIRE(idx_width == 4 || idx_width == 8, SRB_ERR_INVALID_ARG, "idx_width must be 4 or 8");
+    SRB_REQUIRE(offsets && (nnz == 0 || (indices && values)), SRB_ERR_INVALID_ARG, "null array");
+    SRB_REQUIRE(dtype != SRB_I64 && dtype != SRB_U64 && dtype >= 0 && dtype <= SRB_F64, SRB_ERR_UNSUPPORTED_DTYPE,
+                "dtype not supported (the reference panics for I64/U64/Usize/Bool/String, shared/mod.rs:117-126)");
+    SRB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const uint64_t nmajor = format == SRB_CSR ? nrows : ncols;
+    const uint64_t nminor = format == SRB_CSR ? ncols : nrows;
+    SRB_REQUIRE(nminor < (1ull << 32) && nmajor < (1ull << 40), SRB_ERR_INVALID_ARG, "matrix too large");
+    auto st = std::make_shared<Structure>();
+    st->nmajor = nmajor, st->nminor = nminor, st->nnz = nnz;
+    st->offsets = dev_alloc(s, sizeof(int64_t) * (nmajor + 1));
+    st->indices = dev_alloc(s, sizeof(uint32_t) * (nnz ? nnz : 1));
+    Buf flags = dev_zeros(s, sizeof(uint32_t) * 2);
+    if (idx_width == 8) {
+        // u64 -> i64 is a bit copy
+        SRB_CUDA(cudaMemcpyAsync(st->offsets->p, offsets, sizeof(int64_t) * (nmajor + 1), cudaMemcpyHostToDevice, s));
+    } else {
+        upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
+    }
+    const int up_mode = effective_upload_mode(ctx, nnz);
+    const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES || up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ||
+                        up_mode == SRB_UPLOAD_HOST_PACK_DELTA;
+    if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
+    std::unique_ptr<srb_mat> m(new srb_mat());
+    m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
+    m->src_dtype = dtype;
+    m->global_row0 = 0, m->global_nrows = nrows;
+    const bool f32_exact = dtype == SRB_I8 || dtype == SRB_U8 || dtype == SRB_I16 || dtype == SRB_U16 || dtype == SRB_F32;
+    m->vdtype = f32_exact ? SRB_F32 : SRB_F64;
+    m->values = dev_alloc(s, (f32_exact ? 4 : 8) * (nnz ? nnz : 1));
+    // values whose host dtype is the device storage dtype travel as they are, interleaved with the index chunks
+    const bool direct = (dtype == SRB_F32 && f32_exact) || (dtype == SRB_F64 && !f32_exact);
+    uint64_t link_bytes = 0;
+    if (packed)
+        link_bytes = upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
+                                   direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p,
+                                   up_mode == SRB_UPLOAD_HOST_PACK_VALUES ? 1 : up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ? 2 : 0,
+                                   up_mode == SRB_UPLOAD_HOST_PACK_DELTA ? offsets : nullptr, nmajor, st->offsets->as<int64_t>());
+    if (!(packed && direct)) {
+        if (f32_exact) upload_convert<float>(ctx, values, dtype, nnz, m->values->as<float>());
+        else upload_convert<double>(ctx, values, dtype, nnz, m->values->as<double>());
+    }
+    {
+        static const size_t esz[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+        ctx->last_upload_h2d = (uint64_t)idx_width * (nmajor + 1) +
+                               (packed ? link_bytes + (direct ? 0 : esz[dtype] * nnz) : ((uint64_t)idx_width + esz[dtype]) * nnz);
+        ctx->last_upload_packed = packed ? 1 : 0;
+    }
+    if (nmajor) SRB_LAUNCH(canonical_check_kernel, grid_for(ctx, nmajor * 32), 256, 0, s, st->offsets->as<int64_t>(), st->indices->as<uint32_t>(), nmajor, nnz, flags->as<uint32_t>());
+    uint32_t hflags[2];
+    int64_t last = 0;
+    SRB_CUDA(cudaMemcpyAsync(hflags, flags->p, sizeof(hflags), cudaMemcpyDeviceToHost, s));
+    SRB_CUDA(cudaMemcpyAsync(&last, st->offsets->as<int64_t>() + nmajor, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    SRB_CUDA(cudaStreamSynchronize(s));
+    SRB_REQUIRE(!hflags[0], SRB_ERR_INDEX_OOB, "minor index out of bounds");
+    SRB_REQUIRE((uint64_t)last == nnz, SRB_ERR_INVALID_ARG, "offsets[nmajor] != nnz");
+    SRB_REQUIRE(!hflags[1], SRB_ERR_UNSUPPORTED, "non-canonical matrix (unsorted/duplicate indices or non-monotone offsets): the reference answers CsrNonCanonical with todo!()");
+    *out = m.release();
+    SRB_API_END
+}
+
+}  // extern "C"
