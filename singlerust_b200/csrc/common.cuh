@@ -110,7 +110,7 @@ struct srb_ctx {
     void *solver_params = nullptr;
     cudaStream_t eig_stream = nullptr;
     cudaEvent_t eig_in = nullptr, eig_out = nullptr;
-    // pinned staging ring of the packed upload path (api.cu: upload_packed), lazily allocated
+    // pinned staging ring of the packed upload path (upload.cu: upload_packed), lazily allocated
     static constexpr int kUpSlots = 4;
     int upload_mode = -1;  // srb_upload_mode, -1 = the process default (SRB_UPLOAD_PACK)
     uint64_t last_upload_h2d = 0;  // bytes the last srb_mat_upload moved over the link

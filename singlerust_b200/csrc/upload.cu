@@ -12,7 +12,7 @@
 #include "common.cuh"
 #include "host_pack.h"
 
-// built-in default of SRB_UPLOAD_PACK (kept in step with _ffi.UPLOAD_DEFAULT)
+// built-in default of SRB_UPLOAD_PACK
 #define SRB_UPLOAD_DEFAULT_MODE SRB_UPLOAD_AUTO
 
 namespace srb {

@@ -161,7 +161,7 @@ def test_delta_large_multithreaded_matches_single_thread():
 
 
 def warp_decode_emulation(offsets, codes, esc_pos, esc_val):
-    """Lane-by-lane emulation of api.cu: delta_decode_kernel (32-lane segmented inclusive scan with __shfl_up, an escape
+    """Lane-by-lane emulation of upload.cu: delta_decode_kernel (32-lane segmented inclusive scan with __shfl_up, an escape
     restarts the running sum, the last lane's result carries into the next 32 entries of the line)."""
     out = np.zeros(codes.shape[0], np.uint64)
     esc = dict(zip(esc_pos.tolist(), esc_val.tolist()))
