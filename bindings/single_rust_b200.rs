@@ -6,6 +6,7 @@ use std::os::raw::{c_char, c_void};
 #[repr(C)] pub struct srb_ctx { _p: [u8; 0] }
 #[repr(C)] pub struct srb_mat { _p: [u8; 0] }
 #[repr(C)] pub struct srb_stream { _p: [u8; 0] }
+#[repr(C)] pub struct srb_pca_stream { _p: [u8; 0] }
 
 pub const SRB_ROW: i32 = 0;      // Direction::Row    (src/shared/mod.rs:39-42)
 pub const SRB_COLUMN: i32 = 1;   // Direction::Column
@@ -75,6 +76,15 @@ extern "C" {
     pub fn srb_pipeline_normalize_hvg_pca(m: *mut srb_mat, target_sum: f64, n_top: u64, k: u64, center: i32, scale: i32,
                                           gram_mode: i32, hvg_out: *mut u64, scores: *mut f64, components: *mut f64,
                                           evr: *mut f64) -> i32;
+
+    pub fn srb_gene_moments(chunk: *mut srb_mat, count: *mut f64, sum: *mut f64, sumsq: *mut f64) -> i32;
+    pub fn srb_pca_stream_begin(ctx: *mut srb_ctx, ncols: u64, ncells_total: u64, gene_sum: *const f64, gene_sumsq: *const f64,
+                                col_sel: *const u64, n_sel: u64, k: u64, center: i32, scale: i32, gram_mode: i32,
+                                out: *mut *mut srb_pca_stream) -> i32;
+    pub fn srb_pca_stream_push_gram(ps: *mut srb_pca_stream, chunk: *mut srb_mat) -> i32;
+    pub fn srb_pca_stream_fit(ps: *mut srb_pca_stream, components: *mut f64, evr: *mut f64) -> i32;
+    pub fn srb_pca_stream_transform(ps: *mut srb_pca_stream, chunk: *mut srb_mat, scores: *mut f64) -> i32;
+    pub fn srb_pca_stream_free(ps: *mut srb_pca_stream) -> i32;
 
     pub fn srb_stream_begin(ctx: *mut srb_ctx, format: i32, nrows_total: u64, ncols_total: u64,
                             out: *mut *mut srb_stream) -> i32;

@@ -279,6 +279,17 @@ public:
         return {std::move(mn), std::move(mx)};
     }
 
+    /// count, sum and sum of squares per gene of the current values of this CSR (chunk): pass 1 of the out-of-core pipeline
+    struct GeneMoments {
+        std::vector<double> count, sum, sumsq;
+    };
+    GeneMoments gene_moments() const {
+        const size_t m = (size_t)info().ncols;
+        GeneMoments g{std::vector<double>(m), std::vector<double>(m), std::vector<double>(m)};
+        detail::check(srb_gene_moments(h_, g.count.data(), g.sum.data(), g.sumsq.data()));
+        return g;
+    }
+
     void normalize_total_inplace(double target_sum, shared::Direction d) {
         detail::check(srb_normalize_total_inplace(h_, target_sum, (int32_t)d));
     }
@@ -870,7 +881,96 @@ std::vector<double> compute_variance(Device &dev, const ChunkSource<T> &adata, D
 }
 }  // namespace statistics
 
+/// RAII over srb_pca_stream: out-of-core PCA over CSR row chunks (push_gram every chunk, fit, transform every chunk)
+class PcaStream {
+    srb_pca_stream *h_ = nullptr;
+    size_t n_sel_, k_;
+
+public:
+    PcaStream(Device &dev, uint64_t ncols, uint64_t ncells_total, const std::vector<double> &gene_sum, const std::vector<double> &gene_sumsq,
+              const std::vector<uint64_t> &sel, size_t k, bool center, bool scale, int32_t gram_mode = 0)
+        : n_sel_(sel.size()), k_(std::min(k, sel.size())) {
+        if (gene_sum.size() != ncols || gene_sumsq.size() != ncols) throw Error(SRB_ERR_INVALID_ARG, "gene moments must have one entry per gene");
+        detail::check(srb_pca_stream_begin(dev.handle(), ncols, ncells_total, gene_sum.data(), gene_sumsq.data(), sel.data(), sel.size(), k_,
+                                           center, scale, gram_mode, &h_));
+    }
+    ~PcaStream() { srb_pca_stream_free(h_); }
+    PcaStream(const PcaStream &) = delete;
+    PcaStream &operator=(const PcaStream &) = delete;
+    size_t k() const { return k_; }
+    void push_gram(const DeviceMatrix &chunk) { detail::check(srb_pca_stream_push_gram(h_, chunk.handle())); }
+    /// returns (components n_sel x k, explained-variance ratio k)
+    std::pair<Array2, std::vector<double>> fit() {
+        Array2 comps{n_sel_, k_, std::vector<double>(n_sel_ * k_)};
+        std::vector<double> evr(k_);
+        detail::check(srb_pca_stream_fit(h_, comps.data.data(), evr.data()));
+        return {std::move(comps), std::move(evr)};
+    }
+    /// scores of the chunk's rows into out[0 .. rows * k)
+    void transform(const DeviceMatrix &chunk, double *out) { detail::check(srb_pca_stream_transform(h_, chunk.handle(), out)); }
+};
+
 namespace processing {
+/// select_features (dim_red/mod.rs:123-156, HighlyVariable arm) on per-gene moments accumulated over chunks: nonzero-only
+/// one-pass variance (helper/csr.rs:172-186), stable descending sort, ties keep ascending index. O(genes) on the host,
+/// like the reference's own sort.
+inline std::vector<uint64_t> select_hvg_from_moments(const std::vector<double> &count, const std::vector<double> &sum,
+                                                     const std::vector<double> &sumsq, size_t n_top) {
+    const size_t m = count.size();
+    std::vector<double> var(m, 0.0);
+    for (size_t j = 0; j < m; ++j)
+        if (count[j] > 0) {
+            const double mean = sum[j] / count[j];
+            var[j] = sumsq[j] / count[j] - mean * mean;
+            if (std::isnan(var[j])) throw Error(SRB_ERR_NAN, "NaN variance in the HVG sort (the reference panics here)");
+        }
+    std::vector<uint64_t> idx(m);
+    std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return var[a] > var[b]; });
+    idx.resize(std::min(n_top, m));
+    return idx;
+}
+
+/// The headline pipeline for data that does NOT fit the GPU: three passes over the CSR row chunks, one chunk resident at
+/// a time (srb_gene_moments, srb_pca_stream_*). New functionality: the reference's src/backed/processing/mod.rs is empty.
+struct OutOfCoreResult {
+    Array2 scores, components;
+    std::vector<double> explained_variance_ratio;
+    std::vector<uint64_t> selection;
+};
+template <class T>
+OutOfCoreResult normalize_hvg_pca_out_of_core(Device &dev, const ChunkSource<T> &adata, ComputationMode mode, double target_sum = 1e4,
+                                              size_t n_top_genes = 2000, size_t n_components = 50, bool center = true, bool scale = true,
+                                              int32_t gram_mode = 0) {
+    if (mode.is_whole() || adata.format() != Format::Csr) throw Error(SRB_ERR_INVALID_ARG, "the out-of-core pipeline streams CSR row chunks");
+    const uint64_t n = adata.n_obs(), m = adata.n_vars();
+    auto transformed = [&](const CsView<T> &c) {
+        DeviceMatrix d = DeviceMatrix::upload(dev, c);
+        d.normalize_total_inplace(target_sum, Direction::Row);  // row-local: a row chunk normalises like the whole matrix
+        d.log1p_inplace();
+        return d;
+    };
+    std::vector<double> cnt(m, 0.0), sum(m, 0.0), sq(m, 0.0);
+    adata.for_each_chunk(*mode.chunk, [&](const CsView<T> &c) {  // pass 1
+        const auto g = transformed(c).gene_moments();
+        for (uint64_t j = 0; j < m; ++j) cnt[j] += g.count[j], sum[j] += g.sum[j], sq[j] += g.sumsq[j];
+    });
+    OutOfCoreResult r;
+    r.selection = select_hvg_from_moments(cnt, sum, sq, n_top_genes);
+    if (r.selection.size() < 2) throw Error(SRB_ERR_INVALID_ARG, "pca needs at least two selected features (the reference panics here)");
+    PcaStream ps(dev, m, n, sum, sq, r.selection, n_components, center, scale, gram_mode);
+    adata.for_each_chunk(*mode.chunk, [&](const CsView<T> &c) { ps.push_gram(transformed(c)); });  // pass 2
+    auto fit = ps.fit();
+    r.components = std::move(fit.first), r.explained_variance_ratio = std::move(fit.second);
+    r.scores = Array2{(size_t)n, ps.k(), std::vector<double>((size_t)n * ps.k())};
+    uint64_t row = 0;
+    adata.for_each_chunk(*mode.chunk, [&](const CsView<T> &c) {  // pass 3
+        ps.transform(transformed(c), r.scores.data.data() + row * ps.k());
+        row += c.nrows;
+    });
+    return r;
+}
+
 /// Stream the backed X to the device chunk by chunk and keep it resident (srb_stream_set_retain): new functionality,
 /// the reference's src/backed/processing/mod.rs is empty.
 template <class T>

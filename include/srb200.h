@@ -241,6 +241,27 @@ int32_t srb_pipeline_normalize_hvg_pca(srb_mat *m, double target_sum, uint64_t n
                                        int32_t scale, int32_t gram_mode, uint64_t *hvg_out, double *scores,
                                        double *components, double *explained_variance_ratio);
 
+/* ---- out-of-core PCA over CSR row chunks (new: SURVEY §8f N1 / BASELINE.json config 5; the reference's chunk drivers
+ * stop at number / sum, src/shared/statistics/mod.rs:17-83, and src/backed/processing/mod.rs is empty) -------------------
+ * Three passes over the chunks of a data set that does not fit HBM; a chunk is an srb_mat uploaded by the caller with the
+ * transforms already requested (srb_normalize_total_inplace(Row) / srb_log1p_inplace are row-local, so a row chunk
+ * transforms exactly like the whole matrix):
+ *   pass 1  srb_gene_moments(chunk): count, sum, sum of squares per gene of the chunk's current values; the caller adds the
+ *           O(genes) vectors over the chunks and selects the features as select_features does (dim_red/mod.rs:123-156)
+ *   pass 2  srb_pca_stream_begin(global moments, selection) ... srb_pca_stream_push_gram(chunk) ... srb_pca_stream_fit
+ *           (on a multi-rank ctx each rank pushes its own chunks and fit allreduces the Gram matrix)
+ *   pass 3  srb_pca_stream_transform(chunk) -> scores of the chunk's rows (chunk rows x k, row-major)
+ * Results equal srb_pca on the whole matrix up to the summation order of the Gram matrix. */
+typedef struct srb_pca_stream srb_pca_stream;
+int32_t srb_gene_moments(srb_mat *chunk, double *count, double *sum, double *sumsq); /* each ncols long; may be NULL */
+int32_t srb_pca_stream_begin(srb_ctx *ctx, uint64_t ncols, uint64_t ncells_total, const double *gene_sum,
+                             const double *gene_sumsq, const uint64_t *col_sel, uint64_t n_sel, uint64_t k, int32_t center,
+                             int32_t scale, int32_t gram_mode, srb_pca_stream **out);
+int32_t srb_pca_stream_push_gram(srb_pca_stream *ps, srb_mat *chunk);
+int32_t srb_pca_stream_fit(srb_pca_stream *ps, double *components /* n_sel x k */, double *explained_variance_ratio /* k */);
+int32_t srb_pca_stream_transform(srb_pca_stream *ps, srb_mat *chunk, double *scores /* chunk rows x k */);
+int32_t srb_pca_stream_free(srb_pca_stream *ps);
+
 /* per-stage device times (ms) of the last srb_pca / srb_pipeline_* call on this matrix's ctx, measured with
  * CUDA events on the ctx stream: [0] row sums, [1] fused normalise+log1p+gene moments, [2] hvg select,
  * [3] densify, [4] gram, [5] eig, [6] scores, [7] moments allreduce, [8] gram allreduce. n = capacity of out_ms. */

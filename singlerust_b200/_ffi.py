@@ -94,6 +94,12 @@ def lib() -> C.CDLL:
             "srb_pca": [vp, vp, u64, u64, i32, i32, i32, vp, vp, vp],
             "srb_pipeline_normalize_hvg_pca": [vp, f64, u64, u64, i32, i32, i32, vp, vp, vp, vp],
             "srb_last_stage_ms": [vp, vp, i32],
+            "srb_gene_moments": [vp, vp, vp, vp],
+            "srb_pca_stream_begin": [vp, u64, u64, vp, vp, vp, u64, u64, i32, i32, i32, C.POINTER(vp)],
+            "srb_pca_stream_push_gram": [vp, vp],
+            "srb_pca_stream_fit": [vp, vp, vp],
+            "srb_pca_stream_transform": [vp, vp, vp],
+            "srb_pca_stream_free": [vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -368,6 +374,13 @@ class DeviceMatrix:
                                            "std_dev_per_gene")]))
         return o
 
+    def gene_moments(self):
+        """(count, sum, sum of squares) per gene of the current values of this CSR (chunk); never reduced over ranks."""
+        nc = self.shape[1]
+        cnt, s, q = np.zeros(nc), np.zeros(nc), np.zeros(nc)
+        check(lib().srb_gene_moments(self._h, _ptr(cnt), _ptr(s), _ptr(q)))
+        return cnt, s, q
+
     # ---- transforms ----
     def normalize_total_inplace(self, target_sum, direction=ROW):
         check(lib().srb_normalize_total_inplace(self._h, float(target_sum), direction))
@@ -416,6 +429,40 @@ class DeviceMatrix:
         check(lib().srb_pipeline_normalize_hvg_pca(self._h, float(target_sum), n_top, k, int(center), int(scale), gram_mode,
                                                    _ptr(hvg), _ptr(scores), _ptr(comps), _ptr(evr)))
         return dict(scores=scores, components=comps, explained_variance_ratio=evr, selection=hvg)
+
+
+class PcaStream:
+    """Out-of-core PCA over CSR row chunks (srb_pca_stream_*): push_gram every chunk, fit, then transform every chunk."""
+
+    def __init__(self, ctx, ncols, ncells_total, gene_sum, gene_sumsq, col_sel, k, center=True, scale=True, gram_mode=GRAM_TENSOR):
+        self.ctx = ctx
+        self.sel = np.ascontiguousarray(col_sel, np.uint64)
+        self.k = min(int(k), self.sel.size)
+        gs, gq = np.ascontiguousarray(gene_sum, np.float64), np.ascontiguousarray(gene_sumsq, np.float64)
+        assert gs.shape == (ncols,) and gq.shape == (ncols,)
+        self._h = C.c_void_p()
+        check(lib().srb_pca_stream_begin(ctx._h, ncols, ncells_total, _ptr(gs), _ptr(gq), _ptr(self.sel), self.sel.size, self.k,
+                                         int(center), int(scale), gram_mode, C.byref(self._h)))
+
+    def push_gram(self, chunk: "DeviceMatrix"):
+        check(lib().srb_pca_stream_push_gram(self._h, chunk._h))
+
+    def fit(self):
+        comps, evr = np.zeros((self.sel.size, self.k)), np.zeros(self.k)
+        check(lib().srb_pca_stream_fit(self._h, _ptr(comps), _ptr(evr)))
+        return comps, evr
+
+    def transform(self, chunk: "DeviceMatrix", out=None):
+        n = chunk.shape[0]
+        out = np.zeros((n, self.k)) if out is None else out
+        assert out.shape == (n, self.k) and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+        check(lib().srb_pca_stream_transform(self._h, chunk._h, _ptr(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            check(lib().srb_pca_stream_free(self._h))
+            self._h = C.c_void_p()
 
 
 class ChunkStream:

@@ -7,6 +7,8 @@ data. A 10M-cell x 30k-gene data set (15 G nnz = 180 GB at 12 B/nnz) row-sharded
 Data sets beyond the GPUs' HBM would need the multi-pass form (moments -> Gram -> scores over re-read chunks)."""
 from __future__ import annotations
 
+import numpy as np
+
 from .. import _ffi
 from ..anndata import BackedAnnData, IMAnnData
 from ..memory import processing as mem_processing
@@ -35,3 +37,71 @@ def normalize_hvg_pca(ctx: _ffi.Context, adata: BackedAnnData, mode: Computation
     mem_processing.log1p_transform_inplace(dev)
     mem_processing.pca_inplace(dev, n_components, center, scale, None, FeatureSelection.HighlyVariable(n_top_genes))
     return dev
+
+
+def _upload_transformed(ctx, ch, is_csr, target_sum, log1p):
+    ch = ch.tocsr() if is_csr else ch.tocsc()
+    ch.sort_indices()
+    m = _ffi.DeviceMatrix.from_scipy(ctx, ch)
+    if target_sum is not None:
+        m.normalize_total_inplace(target_sum, int(Direction.Row))   # row-local: a row chunk normalises like the whole matrix
+    if log1p:
+        m.log1p_inplace()
+    return m
+
+
+def select_from_moments(count, total, sumsq, feature_selection: FeatureSelection):
+    """select_features (dim_red/mod.rs:123-156) on per-gene moments accumulated over chunks: nonzero-only one-pass variance
+    (helper/csr.rs:172-186), stable descending sort for HighlyVariable (ties keep ascending index), `v > t` for the
+    threshold. O(genes) bookkeeping, on the host like the reference's own sort."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = np.where(count > 0, total / np.maximum(count, 1), 0.0)
+        var = np.where(count > 0, sumsq / np.maximum(count, 1) - mean * mean, 0.0)
+    fs = feature_selection
+    if fs.kind == "HighlyVariable":
+        if np.isnan(var).any():
+            raise ValueError("NaN variance in the HVG sort (the reference panics here)")
+        return np.argsort(-(var + 0.0), kind="stable")[:fs.value].astype(np.uint64), var
+    if fs.kind == "VarianceThreshold":
+        return np.nonzero(var > fs.value)[0].astype(np.uint64), var
+    if fs.kind == "None":
+        return np.arange(var.size, dtype=np.uint64), var
+    raise ValueError(f"{fs.kind} is not available for out-of-core data")
+
+
+def normalize_hvg_pca_out_of_core(ctx: _ffi.Context, adata: BackedAnnData, mode: ComputationMode, target_sum: float = 1e4,
+                                  n_top_genes: int = 2000, n_components: int = 50, center: bool = True, scale: bool = True,
+                                  gram_mode: int = _ffi.GRAM_TENSOR):
+    """The headline pipeline for data that does NOT fit the GPU: three passes over the row chunks of a CSR store, only one
+    chunk resident at a time (srb_gene_moments / srb_pca_stream_*). Returns dict(scores n_obs x k, components n_sel x k,
+    explained_variance_ratio, selection, gene_variance)."""
+    if mode.is_whole or not adata.is_csr:
+        raise ValueError("the out-of-core pipeline streams CSR row chunks (ComputationMode.Chunked)")
+    n, m = adata.n_obs, adata.n_vars
+    cnt, tot, sq = np.zeros(m), np.zeros(m), np.zeros(m)
+    for ch, _s, _e in adata.iter_chunks(mode.chunk):                      # pass 1: per-gene moments of the transformed values
+        dm = _upload_transformed(ctx, ch, True, target_sum, True)
+        c, s, q = dm.gene_moments()
+        cnt += c
+        tot += s
+        sq += q
+        dm.free()
+    sel, var = select_from_moments(cnt, tot, sq, FeatureSelection.HighlyVariable(n_top_genes))
+    if sel.size < 2:
+        raise ValueError("pca needs at least two selected features (the reference panics here)")
+    k = min(int(n_components), sel.size)
+    ps = _ffi.PcaStream(ctx, m, n, tot, sq, sel, k, center, scale, gram_mode)
+    try:
+        for ch, _s, _e in adata.iter_chunks(mode.chunk):                  # pass 2: Gram matrix
+            dm = _upload_transformed(ctx, ch, True, target_sum, True)
+            ps.push_gram(dm)
+            dm.free()
+        comps, evr = ps.fit()
+        scores = np.zeros((n, k))
+        for ch, s0, e0 in adata.iter_chunks(mode.chunk):                  # pass 3: scores
+            dm = _upload_transformed(ctx, ch, True, target_sum, True)
+            ps.transform(dm, scores[s0:e0])
+            dm.free()
+    finally:
+        ps.free()
+    return dict(scores=scores, components=comps, explained_variance_ratio=evr, selection=sel, gene_variance=var)

@@ -456,6 +456,31 @@ int32_t srb_qc_all(srb_mat *m, uint32_t *num_per_cell, uint32_t *num_per_gene, d
     SRB_API_END
 }
 
+// per-gene moments of the CURRENT values of a CSR row chunk (pending transforms applied): count, sum, sum of squares.
+// Chunk-local: never reduced over ranks (pass 1 of the out-of-core pipeline adds them up itself).
+int32_t srb_gene_moments(srb_mat *m, double *count, double *sum, double *sumsq) {
+    SRB_API_BEGIN
+    check_mat(m);
+    SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "gene moments of a chunk need CSR (genes = minor axis)");
+    srb_ctx *c = m->ctx;
+    SRB_CUDA(cudaSetDevice(c->device));
+    const int saved_ranks = c->nranks;
+    c->nranks = 1;
+    try {
+        ensure_minor_moments(m);
+    } catch (...) {
+        c->nranks = saved_ranks;
+        throw;
+    }
+    c->nranks = saved_ranks;
+    const size_t bytes = sizeof(double) * m->ncols;
+    if (count) d2h(c, count, m->minor.cnt->p, bytes);
+    if (sum) d2h(c, sum, m->minor.sum->p, bytes);
+    if (sumsq) d2h(c, sumsq, m->minor.sq->p, bytes);
+    SRB_CUDA(cudaStreamSynchronize(c->stream));
+    SRB_API_END
+}
+
 // ---- normalisation / transform -------------------------------------------------------------------------
 int32_t srb_normalize_total_inplace(srb_mat *m, double target_sum, int32_t direction) {
     SRB_API_BEGIN

@@ -488,3 +488,204 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
 }
 
 }  // namespace srb
+
+// =====================================================================================================================
+// Out-of-core PCA (BASELINE.json config 5): the same kernels, driven chunk by chunk for data that does not
+// fit the GPUs' HBM. The reference has no chunked PCA (src/backed/processing/mod.rs is empty; its chunk drivers stop at
+// number / sum, src/shared/statistics/mod.rs:17-83). Three passes over the row chunks, all arithmetic on the device:
+//   1. per-gene moments of the transformed chunk (srb_gene_moments) — the caller adds the O(genes) vectors and picks the
+//      features exactly like select_features does (dim_red/mod.rs:123-156);
+//   2. srb_pca_stream_push_gram: standardise the chunk with the GLOBAL mean / std (K6) and add its Gram matrix (K7);
+//      srb_pca_stream_fit: correlation matrix, eigenpairs (K8), loadings and explained-variance ratio;
+//   3. srb_pca_stream_transform: scores of a chunk (K6 + K9).
+// =====================================================================================================================
+struct srb_pca_stream {
+    srb_ctx *ctx = nullptr;
+    uint64_t M = 0, n_sel = 0, k = 0, rows_seen = 0;
+    double n_cells = 0.0;
+    bool center = true, scale = true, fitted = false;
+    int gram_mode = 0;
+    uint32_t dpad = 0, kpad = 0;
+    srb::Buf sel, sum, sq, lut16, shis, zc_h, zc_l, shift, inv_sd, flag, G, W, comps, evr;
+};
+
+namespace srb {
+
+__global__ void add_inplace_kernel(double *__restrict__ acc, const double *__restrict__ x, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc[i] += x[i];
+}
+
+// K6 for one chunk with the stream's global statistics: panels Xh / Xl (chunk rows x dpad)
+static void stream_densify(srb_pca_stream *ps, srb_mat *m, Buf &Xh, Buf &Xl) {
+    srb_ctx *c = ps->ctx;
+    cudaStream_t s = c->stream;
+    const uint64_t n = m->nrows;
+    const uint32_t dpad = ps->dpad;
+    Xh = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad), Xl = dev_alloc(s, 2 * (size_t)std::max<uint64_t>(n, 1) * dpad);
+    if (!n) return;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8 * 4);
+    if (m->vdtype == SRB_F32)
+        SRB_LAUNCH((densify_panels_pipe_kernel<float>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+    else
+        SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+}
+
+static void stream_check_chunk(const srb_pca_stream *ps, const srb_mat *m) {
+    SRB_REQUIRE(ps && m && m->ctx && m->st, SRB_ERR_INVALID_ARG, "null handle");
+    SRB_REQUIRE(m->ctx == ps->ctx, SRB_ERR_INVALID_ARG, "chunk and PCA stream belong to different contexts");
+    SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "out-of-core PCA takes CSR row chunks");
+    SRB_REQUIRE(m->ncols == ps->M, SRB_ERR_INVALID_ARG, "chunk has a different number of genes");
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" {
+
+int32_t srb_pca_stream_begin(srb_ctx *ctx, uint64_t ncols, uint64_t ncells_total, const double *gene_sum, const double *gene_sumsq,
+                             const uint64_t *col_sel, uint64_t n_sel, uint64_t k, int32_t center, int32_t scale, int32_t gram_mode,
+                             srb_pca_stream **out) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx && out && gene_sum && gene_sumsq && col_sel, SRB_ERR_INVALID_ARG, "null argument");
+    SRB_REQUIRE(gram_mode == 0 || gram_mode == 1, SRB_ERR_INVALID_ARG, "gram_mode must be 0 (tcgen05) or 1 (fp64)");
+    SRB_REQUIRE(ncells_total >= 2, SRB_ERR_INVALID_ARG, "PCA needs at least two cells");
+    SRB_REQUIRE(n_sel >= 1 && n_sel < 65535 && k >= 1 && k <= n_sel, SRB_ERR_INVALID_ARG, "need 1 <= k <= n_sel < 65535");
+    SRB_REQUIRE(ncols < (1ull << 32), SRB_ERR_INVALID_ARG, "too many genes");
+    SRB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    std::vector<uint32_t> h(n_sel);
+    for (uint64_t i = 0; i < n_sel; ++i) {
+        SRB_REQUIRE(col_sel[i] < ncols, SRB_ERR_INDEX_OOB, "Index out of bounds");
+        h[i] = (uint32_t)col_sel[i];
+    }
+    std::unique_ptr<srb_pca_stream> ps(new srb_pca_stream());
+    ps->ctx = ctx, ps->M = ncols, ps->n_sel = n_sel, ps->k = k, ps->n_cells = (double)ncells_total;
+    ps->center = center != 0, ps->scale = scale != 0, ps->gram_mode = gram_mode;
+    const uint32_t dpad = ps->dpad = (uint32_t)((n_sel + 255) / 256 * 256);
+    ps->kpad = (uint32_t)((k + 63) / 64 * 64);
+    const uint64_t M = ncols;
+    ps->sel = dev_alloc(s, 4 * n_sel), ps->sum = dev_alloc(s, 8 * (M + 1)), ps->sq = dev_alloc(s, 8 * (M + 1));
+    SRB_CUDA(cudaMemcpyAsync(ps->sel->p, h.data(), 4 * n_sel, cudaMemcpyHostToDevice, s));
+    if (M) {
+        SRB_CUDA(cudaMemcpyAsync(ps->sum->p, gene_sum, 8 * M, cudaMemcpyHostToDevice, s));
+        SRB_CUDA(cudaMemcpyAsync(ps->sq->p, gene_sumsq, 8 * M, cudaMemcpyHostToDevice, s));
+    }
+    Buf lut = dev_alloc(s, 4 * (M + 1));
+    SRB_LAUNCH(lut_fill_kernel, nb(M), 256, 0, s, lut->as<int>(), M);
+    SRB_LAUNCH(lut_set_kernel, nb(n_sel), 256, 0, s, lut->as<int>(), ps->sel->as<uint32_t>(), n_sel);
+    ps->flag = dev_zeros(s, 4);
+    ps->shift = dev_alloc(s, 8 * dpad), ps->inv_sd = dev_alloc(s, 8 * dpad), ps->zc_h = dev_alloc(s, 2 * dpad), ps->zc_l = dev_alloc(s, 2 * dpad);
+    Buf shf = dev_alloc(s, 4 * dpad), isf = dev_alloc(s, 4 * dpad);
+    SRB_LAUNCH(sel_stats_kernel, nb(dpad), 256, 0, s, ps->sel->as<uint32_t>(), n_sel, dpad, ps->sum->as<double>(), ps->sq->as<double>(),
+               ps->n_cells, ps->center ? 1 : 0, ps->scale ? 1 : 0, ps->shift->as<double>(), ps->inv_sd->as<double>(), shf->as<float>(),
+               isf->as<float>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), ps->flag->as<uint32_t>());
+    ps->lut16 = dev_alloc(s, 2 * (M + 1)), ps->shis = dev_alloc(s, 8 * dpad);
+    SRB_LAUNCH(lut16_kernel, nb(M), 256, 0, s, lut->as<int>(), ps->lut16->as<uint16_t>(), M);
+    SRB_LAUNCH(shis_kernel, nb(dpad), 256, 0, s, shf->as<float>(), isf->as<float>(), ps->shis->as<float2>(), dpad);
+    ps->G = dev_zeros(s, 8 * (size_t)dpad * dpad);
+    SRB_CUDA(cudaStreamSynchronize(s));  // the host staging vectors are done with
+    *out = ps.release();
+    SRB_API_END
+}
+
+int32_t srb_pca_stream_push_gram(srb_pca_stream *ps, srb_mat *chunk) {
+    SRB_API_BEGIN
+    stream_check_chunk(ps, chunk);
+    SRB_REQUIRE(!ps->fitted, SRB_ERR_INVALID_ARG, "push_gram after fit");
+    srb_ctx *c = ps->ctx;
+    SRB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    materialize(chunk, false);  // pending normalise / log1p are applied to the chunk's values
+    const uint64_t n = chunk->nrows;
+    if (n) {
+        const uint32_t dpad = ps->dpad;
+        Buf Xh, Xl;
+        stream_densify(ps, chunk, Xh, Xl);
+        Buf Gc = dev_zeros(s, 8 * (size_t)dpad * dpad);
+        if (ps->gram_mode == 0) {
+            gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, Gc->as<double>());
+        } else {
+            const uint32_t nt = dpad / GT;
+            const uint32_t ntiles = nt * (nt + 1) / 2;
+            uint64_t splits = std::max<uint64_t>(1, std::min<uint64_t>((n + 511) / 512, (uint64_t)c->sm_count * 8 / ntiles + 1));
+            const uint64_t rps = ((n + splits - 1) / splits + GK - 1) / GK * GK;
+            splits = (n + rps - 1) / rps;
+            SRB_LAUNCH(gram_f64_kernel, dim3(ntiles, (unsigned)splits), 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, rps, Gc->as<double>());
+            SRB_LAUNCH(gram_mirror_kernel, nb((uint64_t)dpad * dpad), 256, 0, s, Gc->as<double>(), dpad, (uint32_t)GT);
+        }
+        SRB_LAUNCH(add_inplace_kernel, (unsigned)std::min<uint64_t>(((uint64_t)dpad * dpad + 255) / 256, (uint64_t)c->sm_count * 16), 256, 0, s,
+                   ps->G->as<double>(), Gc->as<double>(), (uint64_t)dpad * dpad);
+        ps->rows_seen += n;
+    }
+    SRB_CUDA(cudaStreamSynchronize(s));
+    SRB_API_END
+}
+
+int32_t srb_pca_stream_fit(srb_pca_stream *ps, double *components, double *explained_variance_ratio) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ps, SRB_ERR_INVALID_ARG, "null handle");
+    SRB_REQUIRE(!ps->fitted, SRB_ERR_INVALID_ARG, "already fitted");
+    srb_ctx *c = ps->ctx;
+    SRB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint64_t n_sel = ps->n_sel, k = ps->k;
+    const uint32_t dpad = ps->dpad, kpad = ps->kpad;
+    if (c->nranks > 1) allreduce_f64_sum(c, ps->G->as<double>(), (size_t)dpad * dpad);  // ranks hold disjoint chunks
+    Buf C = dev_alloc(s, 8 * n_sel * n_sel), evals = dev_alloc(s, 8 * n_sel), tr = dev_alloc(s, 8);
+    ps->comps = dev_alloc(s, 8 * n_sel * k), ps->W = dev_zeros(s, 8 * (size_t)dpad * kpad), ps->evr = dev_alloc(s, 8 * k);
+    SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, ps->G->as<double>(), dpad, n_sel, ps->sel->as<uint32_t>(), ps->sum->as<double>(),
+               ps->sq->as<double>(), ps->shift->as<double>(), ps->inv_sd->as<double>(), ps->n_cells, C->as<double>());
+    SRB_LAUNCH(trace_kernel, 1, 256, 0, s, C->as<double>(), n_sel, tr->as<double>());
+    const uint32_t npairs = sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, (uint32_t)k, evals->as<double>());
+    SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), npairs, n_sel, (uint32_t)k, kpad, tr->as<double>(),
+               ps->comps->as<double>(), ps->W->as<double>(), ps->evr->as<double>());
+    if (components) SRB_CUDA(cudaMemcpyAsync(components, ps->comps->p, 8 * n_sel * k, cudaMemcpyDeviceToHost, s));
+    if (explained_variance_ratio) SRB_CUDA(cudaMemcpyAsync(explained_variance_ratio, ps->evr->p, 8 * k, cudaMemcpyDeviceToHost, s));
+    uint32_t hflag = 0;
+    SRB_CUDA(cudaMemcpyAsync(&hflag, ps->flag->p, 4, cudaMemcpyDeviceToHost, s));
+    SRB_CUDA(cudaStreamSynchronize(s));
+    SRB_REQUIRE(!hflag, SRB_ERR_NAN, "a selected feature has zero variance over all cells while scale=true (the reference divides by zero: NaN scores)");
+    ps->G.reset();
+    ps->fitted = true;
+    SRB_API_END
+}
+
+int32_t srb_pca_stream_transform(srb_pca_stream *ps, srb_mat *chunk, double *scores) {
+    SRB_API_BEGIN
+    stream_check_chunk(ps, chunk);
+    SRB_REQUIRE(ps->fitted, SRB_ERR_INVALID_ARG, "transform before fit");
+    SRB_REQUIRE(scores || chunk->nrows == 0, SRB_ERR_INVALID_ARG, "scores is null");
+    srb_ctx *c = ps->ctx;
+    SRB_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    materialize(chunk, false);
+    const uint64_t n = chunk->nrows, k = ps->k;
+    if (n) {
+        Buf Xh, Xl;
+        stream_densify(ps, chunk, Xh, Xl);
+        Buf out = dev_alloc(s, 8 * n * k);
+        if (ps->gram_mode == 0 && k <= 64) {
+            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, out->as<double>());
+        } else {
+            const unsigned grid = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)c->sm_count * 16);
+            for (uint32_t c0 = 0; c0 < k; c0 += 64)
+                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, c0, out->as<double>());
+        }
+        SRB_CUDA(cudaMemcpyAsync(scores, out->p, 8 * n * k, cudaMemcpyDeviceToHost, s));
+        SRB_CUDA(cudaStreamSynchronize(s));
+    }
+    SRB_API_END
+}
+
+int32_t srb_pca_stream_free(srb_pca_stream *ps) {
+    SRB_API_BEGIN
+    if (ps) {
+        cudaSetDevice(ps->ctx->device);
+        cudaStreamSynchronize(ps->ctx->stream);
+        delete ps;
+    }
+    SRB_API_END
+}
+
+}  // extern "C"

@@ -362,8 +362,56 @@ static void random_checks(Device &dev, Device &faithful) {
     CHECK(all_close(bk.explained_variance_ratio, p.explained_variance_ratio, 1e-12));
 }
 
+// out-of-core pipeline (three passes over row chunks) against the resident one on the same matrix
+static int out_of_core_check() {
+    Device dev(0);
+    CsMatrix<float> a = random_csr(5000, 1200, 0.05, 11);
+    // plant three cell programmes so that the two leading components are well separated
+    for (uint64_t i = 0; i < a.nrows; ++i)
+        for (uint64_t p = a.offsets[i]; p < a.offsets[i + 1]; ++p)
+            if (a.indices[p] % 3 == i % 3) a.values[p] *= 4.0f;
+    backed::HostChunkSource<float> src(a.view());
+    namespace pr = memory::processing;
+    for (int32_t gram_mode : {1, 0}) {  // 1: fp64 Gram (only the summation order differs), 0: tensor cores (1e-6-level Gram)
+        const double tol = gram_mode == 1 ? 1e-8 : 1e-4;
+        IMAnnData ref(dev, a.view());
+        pr::normalize_total_inplace(ref, 1e4, Direction::Row);
+        pr::log1p_transform_inplace(ref);
+        pr::pca_inplace(ref, 2, true, true, std::nullopt, FeatureSelection::HighlyVariable(200), pr::SVDMode::Lapack, gram_mode);
+        auto sel_ref = pr::select_features(ref, FeatureSelection::HighlyVariable(200));
+        for (size_t chunk : {700u, 5000u, 64u}) {
+            auto r = backed::processing::normalize_hvg_pca_out_of_core(dev, src, ComputationMode::Chunked(chunk), 1e4, 200, 2, true, true, gram_mode);
+            CHECK(all_equal(r.selection, sel_ref));
+            CHECK(all_close(r.explained_variance_ratio, ref.explained_variance_ratio, tol));
+            const Array2 &want = ref.obsm["X_pca"];
+            CHECK(r.scores.rows == want.rows && r.scores.cols == 2 && r.components.rows == 200 && r.components.cols == 2);
+            double scale = 0, err = 0;
+            for (size_t c = 0; c < 2; ++c) {
+                double dot = 0;
+                for (size_t i = 0; i < want.rows; ++i) dot += r.scores(i, c) * want(i, c);
+                const double sgn = dot < 0 ? -1.0 : 1.0;
+                for (size_t i = 0; i < want.rows; ++i) {
+                    err = std::max(err, std::fabs(sgn * r.scores(i, c) - want(i, c)));
+                    scale = std::max(scale, std::fabs(want(i, c)));
+                }
+            }
+            CHECK(err <= tol * scale);
+        }
+    }
+    printf("out-of-core: %d checks, %d failed\n", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
     if (argc > 1 && std::string(argv[1]) == "--cpu-check") return cpu_check(argc > 2 ? argv[2] : nullptr);
+    if (argc > 1 && std::string(argv[1]) == "--out-of-core") {
+        try {
+            return out_of_core_check();
+        } catch (const Error &e) {
+            fprintf(stderr, "single_rust::Error %d: %s\n", e.code, e.what());
+            return 2;
+        }
+    }
     if (argc > 3 && std::string(argv[1]) == "--store-sums") {  // per-chunk value sums of a chunk store written by someone else
         backed::StoreChunkSource<float> disk(argv[2]);
         disk.for_each_chunk((size_t)std::atoll(argv[3]), [&](const CsView<float> &c) {
