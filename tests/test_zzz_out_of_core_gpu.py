@@ -38,7 +38,7 @@ def test_out_of_core_equals_resident(env, tmp_path, gram_mode):
     mem.processing.log1p_transform_inplace(ref)
     sel_ref = mem.processing.select_features(ref, env["FS"].HighlyVariable(n_top))
     mem.processing.pca_inplace(ref, k, True, True, None, env["FS"].HighlyVariable(n_top), gram_mode=gram_mode)
-    tol = 1e-8 if gram_mode == 1 else 1e-4          # fp64 Gram: summation order only; tensor-core Gram: 1e-6-level entries
+    tol = 1e-7 if gram_mode == 1 else 1e-4          # fp64 Gram: summation order + 1e-9 moments; tensor-core Gram: 1e-6-level entries
     for chunk in (900, 4000, 97):
         r = env["backed"].processing.normalize_hvg_pca_out_of_core(ctx, disk, env["CM"].Chunked(chunk), 1e4, n_top, k, gram_mode=gram_mode)
         np.testing.assert_array_equal(r["selection"], sel_ref)
@@ -59,7 +59,7 @@ def test_gene_moments_of_a_chunk(env):
     m = ffi.DeviceMatrix.from_scipy(ctx, a)
     cnt, s, q = m.gene_moments()
     d = a.toarray().astype(np.float64)
-    np.testing.assert_array_equal(cnt, (a != 0).sum(axis=0).A1 if hasattr((a != 0).sum(axis=0), "A1") else np.asarray((a != 0).sum(axis=0)).ravel())
+    np.testing.assert_array_equal(cnt, np.asarray((a != 0).sum(axis=0)).ravel())
     np.testing.assert_array_equal(s, d.sum(axis=0))                     # integer counts: exact
     np.testing.assert_array_equal(q, (d * d).sum(axis=0))
     m.normalize_total_inplace(1e4, ffi.ROW)
