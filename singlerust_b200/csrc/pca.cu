@@ -603,7 +603,8 @@ int32_t srb_pca_stream_push_gram(srb_pca_stream *ps, srb_mat *chunk) {
         Buf Xh, Xl;
         stream_densify(ps, chunk, Xh, Xl);
         Buf Gc = dev_zeros(s, 8 * (size_t)dpad * dpad);
-        if (ps->gram_mode == 0) {
+        // a chunk smaller than one tensor-core tile of cells goes through the fp64 CUDA-core Gram (exact, and tiny)
+        if (ps->gram_mode == 0 && n >= 256) {
             gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, Gc->as<double>());
         } else {
             const uint32_t nt = dpad / GT;
@@ -665,7 +666,7 @@ int32_t srb_pca_stream_transform(srb_pca_stream *ps, srb_mat *chunk, double *sco
         Buf Xh, Xl;
         stream_densify(ps, chunk, Xh, Xl);
         Buf out = dev_alloc(s, 8 * n * k);
-        if (ps->gram_mode == 0 && k <= 64) {
+        if (ps->gram_mode == 0 && k <= 64 && n >= 256) {
             scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, out->as<double>());
         } else {
             const unsigned grid = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)c->sm_count * 16);
