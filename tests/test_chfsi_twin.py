@@ -1,6 +1,6 @@
 """The K8 algorithm (Chebyshev-filtered subspace iteration, csrc/eig.cu) checked through its NumPy twin
 (tools/chfsi_twin.py: same flow, constants and update rules) against LAPACK on five kinds of spectrum. The CUDA code is
-compared with cuSOLVER's syevd on the GPU (tests/test_zzz_eig_gpu.py); this test pins the numerical method itself."""
+compared with cuSOLVER's syevd on the GPU (tests/test_zzz1_eig_gpu.py); this test pins the numerical method itself."""
 import os
 import sys
 
