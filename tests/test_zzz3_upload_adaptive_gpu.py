@@ -1,9 +1,15 @@
 """HOST_PACK_ADAPTIVE upload: values are packed only for the chunks during which the host is ahead of the link. Whatever
 mix of packed and raw chunks results, the device matrix must equal the host arrays bit for bit."""
+import os
+
 import numpy as np
 import pytest
 
-pytestmark = pytest.mark.gpu
+# This path was written after round 1's GPU budget was spent: it has compiled and its host side is CPU-tested, but it
+# has never run on a GPU. tools/r2_first_call.sh sets SRB_TEST_PENDING=1 for its first run; once green the gate goes.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SRB_TEST_PENDING") != "1",
+                                 reason="first GPU run pending (round 2): set SRB_TEST_PENDING=1")]
 
 
 def test_adaptive_value_packing_is_lossless():

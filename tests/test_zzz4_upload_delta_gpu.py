@@ -1,13 +1,19 @@
 """HOST_PACK_DELTA upload: the sorted indices of each line cross the link as one-byte gaps (+ an escape list) and are
 rebuilt on the device. The device matrix must equal the caller's arrays exactly, and malformed input must still be
 reported with the same status codes as in the other upload modes."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
 from tests._util import random_csr
 
-pytestmark = pytest.mark.gpu
+# This path was written after round 1's GPU budget was spent: it has compiled and its host side is CPU-tested, but it
+# has never run on a GPU. tools/r2_first_call.sh sets SRB_TEST_PENDING=1 for its first run; once green the gate goes.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SRB_TEST_PENDING") != "1",
+                                 reason="first GPU run pending (round 2): set SRB_TEST_PENDING=1")]
 
 
 @pytest.fixture(scope="module")
