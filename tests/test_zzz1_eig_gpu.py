@@ -3,6 +3,8 @@ same correlation matrix — explained-variance ratios, loadings and scores must 
 tolerance, whichever way the spectrum looks (flat noise, or a few strong cell programmes on top of noise). If the
 iteration declines (breakdown / no convergence) the library falls back to syevd by itself; the results must match
 either way."""
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -11,7 +13,11 @@ from oracle import oracle as O
 from oracle import pca_oracle as P
 from tests._util import sign_align
 
-pytestmark = pytest.mark.gpu
+# Written after round 1's last GPU call: the code path under test has run on the GPU (tools/chfsi_probe.py, the backed
+# pipeline tests), this test file has not. tools/r2_first_call.sh sets SRB_TEST_PENDING=1 for its first run.
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("SRB_TEST_PENDING") != "1",
+                                 reason="first GPU run pending (round 2): set SRB_TEST_PENDING=1")]
 
 
 @pytest.fixture(scope="module")

@@ -1,6 +1,6 @@
 #!/bin/bash
 # First GPU call of round 2 (~4 min of box time): verify everything round 1 could only build, then the tunable sweeps.
-#   1. full GPU suite at defaults (includes the tests added after the last GPU run of round 1: test_zzz1..5; SRB_TEST_PENDING=1 un-gates zzz3..5)
+#   1. full GPU suite at defaults (includes the tests added after the last GPU run of round 1: test_zzz1..5; SRB_TEST_PENDING=1 un-gates them)
 #   2. upload modes A/B at the bench size, incl. the unmeasured HOST_PACK_ADAPTIVE and HOST_PACK_DELTA
 #   3. K8 tunables (each setting needs its own process: they are read once)
 #   4. bench at defaults
