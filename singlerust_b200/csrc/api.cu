@@ -4,6 +4,7 @@
 #include <cmath>
 #include <chrono>
 #include <map>
+#include <set>
 #include <mutex>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +28,22 @@ struct BlockCache {
 };
 static std::mutex g_cache_mu;
 static std::map<cudaStream_t, BlockCache> g_caches;
+static std::set<cudaStream_t> g_live_streams;
+static std::set<const srb_ctx *> g_live_ctx;
+
+void register_stream(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_live_streams.insert(s);
+}
+void unregister_stream(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_live_streams.erase(s);
+    g_caches.erase(s);
+}
+bool ctx_alive(const srb_ctx *c) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    return g_live_ctx.count(c) != 0;
+}
 static constexpr size_t kCacheBudget = 64ull << 30;
 
 static size_t round_block(size_t n) {
@@ -64,6 +81,10 @@ DevBuf::DevBuf(size_t n, cudaStream_t s) : bytes(n), st(s) {
 DevBuf::~DevBuf() {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (!g_live_streams.count(st)) {  // the owning context is gone: nothing may be queued on its stream any more
+        cudaFree(p);
+        return;
+    }
     BlockCache &c = g_caches[st];
     c.free_blocks.emplace(cap, p);
     c.cached_bytes += cap;
@@ -124,7 +145,10 @@ StageTimer::~StageTimer() {
     }
 }
 
-static void check_mat(const srb_mat *m) { SRB_REQUIRE(m && m->ctx && m->st, SRB_ERR_INVALID_ARG, "null matrix handle"); }
+static void check_mat(const srb_mat *m) {
+    SRB_REQUIRE(m && m->ctx && m->st, SRB_ERR_INVALID_ARG, "null matrix handle");
+    SRB_REQUIRE(ctx_alive(m->ctx), SRB_ERR_INVALID_ARG, "the matrix outlived its context (srb_ctx_destroy was called first)");
+}
 static void check_dir(int d) { SRB_REQUIRE(d == SRB_ROW || d == SRB_COLUMN, SRB_ERR_INVALID_ARG, "direction must be 0 (Row) or 1 (Column)"); }
 
 static void d2h(srb_ctx *c, void *host, const void *dev, size_t bytes) {
@@ -212,6 +236,11 @@ int32_t srb_ctx_create(int32_t device, srb_ctx **out) {
         SRB_CUDA(cudaEventCreate(&c->ev0[i]));
         SRB_CUDA(cudaEventCreate(&c->ev1[i]));
     }
+    register_stream(c->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_live_ctx.insert(c.get());
+    }
     *out = c.release();
     SRB_API_END
 }
@@ -219,9 +248,15 @@ int32_t srb_ctx_create(int32_t device, srb_ctx **out) {
 int32_t srb_ctx_destroy(srb_ctx *ctx) {
     SRB_API_BEGIN
     if (!ctx) return SRB_OK;
+    SRB_REQUIRE(ctx_alive(ctx), SRB_ERR_INVALID_ARG, "context already destroyed");
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        g_live_ctx.erase(ctx);
+    }
     release_cached_blocks(ctx->stream);
+    unregister_stream(ctx->stream);
     comm_destroy(ctx);
     eig_destroy(ctx);
     if (ctx->up_ring) cudaFreeHost(ctx->up_ring);
@@ -283,8 +318,8 @@ int32_t srb_mat_set_shard(srb_mat *m, uint64_t global_row0, uint64_t global_nrow
 int32_t srb_mat_free(srb_mat *m) {
     SRB_API_BEGIN
     if (m) {
-        cudaSetDevice(m->ctx->device);
-        delete m;
+        if (ctx_alive(m->ctx)) cudaSetDevice(m->ctx->device);
+        delete m;  // buffers of a dead context go straight back to the driver (~DevBuf)
     }
     SRB_API_END
 }
@@ -464,15 +499,7 @@ int32_t srb_gene_moments(srb_mat *m, double *count, double *sum, double *sumsq) 
     SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "gene moments of a chunk need CSR (genes = minor axis)");
     srb_ctx *c = m->ctx;
     SRB_CUDA(cudaSetDevice(c->device));
-    const int saved_ranks = c->nranks;
-    c->nranks = 1;
-    try {
-        ensure_minor_moments(m);
-    } catch (...) {
-        c->nranks = saved_ranks;
-        throw;
-    }
-    c->nranks = saved_ranks;
+    ensure_minor_moments(m, /*local_only=*/true);
     const size_t bytes = sizeof(double) * m->ncols;
     if (count) d2h(c, count, m->minor.cnt->p, bytes);
     if (sum) d2h(c, sum, m->minor.sum->p, bytes);

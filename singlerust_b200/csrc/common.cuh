@@ -45,8 +45,11 @@ extern std::atomic<uint64_t> g_launches;
         SRB_CUDA(cudaGetLastError());                                                                        \
     } while (0)
 
-// ABI boundary: translate exceptions into status codes + thread-local message
-#define SRB_API_BEGIN try {
+// ABI boundary: translate exceptions into status codes + thread-local message. A non-sticky error left behind by an
+// earlier call of this thread (ours or another library's) is dropped first, so SRB_LAUNCH never reports a stale one.
+#define SRB_API_BEGIN                                                                                        \
+    try {                                                                                                    \
+        (void)cudaGetLastError();
 #define SRB_API_END                                                                                          \
     return SRB_OK;                                                                                           \
     }                                                                                                        \
@@ -63,6 +66,11 @@ extern std::atomic<uint64_t> g_launches;
         return SRB_ERR_INVALID_ARG;                                                                          \
     }
 
+// Handles (matrices, streams) may outlive their context in a garbage-collected host language: contexts and their
+// streams are registered while alive, and a handle freed after its context only gives its memory back to the driver.
+void register_stream(cudaStream_t s);
+void unregister_stream(cudaStream_t s);
+bool ctx_alive(const srb_ctx *c);
 // device buffer owned by one context stream; returned to that stream's block cache when the last reference drops
 void release_cached_blocks(cudaStream_t s);
 struct DevBuf {
@@ -199,8 +207,8 @@ void major_sum_absmax(srb_mat *m);                               // fills m->maj
 void major_variance(srb_mat *m, double *d_out);                  // two-pass per line, NaN for empty
 void major_min_max(srb_mat *m, double *d_min, double *d_max);
 // minor_moments.cu
-void materialize(srb_mat *m, bool want_moments);                 // apply pending transforms (fused with moments)
-void ensure_minor_moments(srb_mat *m);                           // moments of current logical values
+void materialize(srb_mat *m, bool want_moments, bool local_only = false);  // apply pending transforms (fused with moments)
+void ensure_minor_moments(srb_mat *m, bool local_only = false);  // moments of current logical values (local_only: never reduced over ranks)
 void minor_min_max(srb_mat *m, double *d_min, double *d_max);
 void minor_variance_from_moments(srb_mat *m, double *d_out, bool sqrt_it);
 void set_pending_normalize(srb_mat *m, double target, int direction);

@@ -352,6 +352,7 @@ uint32_t sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, uint32_t topk, doub
         int lo = 0, hi = 0;
         SRB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically lowest = highest priority
         SRB_CUDA(cudaStreamCreateWithPriority(&ctx->eig_stream, cudaStreamNonBlocking, hi));
+        register_stream(ctx->eig_stream);
         SRB_CUDA(cudaEventCreateWithFlags(&ctx->eig_in, cudaEventDisableTiming));
         SRB_CUDA(cudaEventCreateWithFlags(&ctx->eig_out, cudaEventDisableTiming));
     }
@@ -382,7 +383,18 @@ uint32_t sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, uint32_t topk, doub
         SRB_CUDA(cudaEventRecord(ctx->eig_in, s));
         SRB_CUDA(cudaStreamWaitEvent(es, ctx->eig_in, 0));
         // the work buffers live in the eig stream's own block cache (allocated, used and released on that stream only)
-        const bool ok = chfsi_topk(ctx, (cublasHandle_t)ctx->blas, h, es, d_C, d, topk, d_evals);
+        bool ok = false;
+        try {
+            ok = chfsi_topk(ctx, (cublasHandle_t)ctx->blas, h, es, d_C, d, topk, d_evals);
+        } catch (...) {
+            // leave the cached handle and the two streams in a defined state before the error travels on: host pointer
+            // mode again, and nothing of the eig stream still in flight when its buffers return to the block caches
+            cublasSetPointerMode((cublasHandle_t)ctx->blas, CUBLAS_POINTER_MODE_HOST);
+            cudaEventRecord(ctx->eig_out, es);
+            cudaStreamWaitEvent(s, ctx->eig_out, 0);
+            cudaStreamSynchronize(es);
+            throw;
+        }
         ctx->last_eig_mode = ok ? 1 : 2;
         SRB_CUDA(cudaEventRecord(ctx->eig_out, es));
         SRB_CUDA(cudaStreamWaitEvent(s, ctx->eig_out, 0));
@@ -450,7 +462,7 @@ uint32_t sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, uint32_t topk, doub
 void eig_destroy(srb_ctx *ctx) {
     if (ctx->blas) cublasDestroy((cublasHandle_t)ctx->blas);
     ctx->blas = nullptr;
-    if (ctx->eig_stream) release_cached_blocks(ctx->eig_stream);
+    if (ctx->eig_stream) release_cached_blocks(ctx->eig_stream), unregister_stream(ctx->eig_stream);
     if (ctx->solver_params) cusolverDnDestroyParams((cusolverDnParams_t)ctx->solver_params);
     ctx->solver_params = nullptr;
     if (ctx->solver) cusolverDnDestroy((cusolverDnHandle_t)ctx->solver);

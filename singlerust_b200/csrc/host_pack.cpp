@@ -5,7 +5,10 @@
 // Pure host code (compiled by g++, no CUDA): marshalling only — no statistic is computed here.
 #include <algorithm>
 #include <atomic>
+#include <sched.h>
+
 #include <condition_variable>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -86,11 +89,29 @@ public:
     }
 };
 
+// CPUs this process may really use: the affinity mask and the cgroup-v2 CPU quota (hardware_concurrency sees neither;
+// a pool larger than the quota only adds context switches).
+static unsigned usable_cpus() {
+    unsigned n = std::max(1u, std::thread::hardware_concurrency());
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = std::min<unsigned>(n, (unsigned)std::max(1, CPU_COUNT(&set)));
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char quota[32] = {0};
+        long period = 0;
+        if (fscanf(f, "%31s %ld", quota, &period) == 2 && strcmp(quota, "max") != 0 && period > 0) {
+            const long q = atol(quota);
+            if (q > 0) n = std::min<unsigned>(n, (unsigned)std::max(1L, q / period));
+        }
+        fclose(f);
+    }
+    return n;
+}
+
 int host_pack_threads() {
     static int n = [] {
         const char *e = getenv("SRB_UPLOAD_THREADS");
         int v = e ? atoi(e) : 0;
-        if (v <= 0) v = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (v <= 0) v = (int)std::min<unsigned>(usable_cpus(), 16u);
         return std::min(v, 64);
     }();
     return n;

@@ -458,7 +458,7 @@ __global__ void decision_pack_kernel(const double *__restrict__ range, const uin
     dec[1] = -range[1];
     dec[2] = (double)flags[0], dec[3] = (double)flags[1], dec[4] = (double)flags[2];
 }
-static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, int out_dtype, Buf &dec_out) {
+static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, int out_dtype, Buf &dec_out, bool reduce) {
     int S;
     uint32_t W;
     stripe_plan(m, &S, &W);
@@ -467,7 +467,7 @@ static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, i
     cudaStream_t s = m->ctx->stream;
     Buf dec = dev_alloc(s, 5 * sizeof(double));
     SRB_LAUNCH(decision_pack_kernel, 1, 1, 0, s, range->as<double>(), m->major.flags->as<uint32_t>(), dec->as<double>());
-    if (m->ctx->nranks > 1 && m->format == SRB_CSR) allreduce_f64_max(m->ctx, dec->as<double>(), 5);
+    if (reduce) allreduce_f64_max(m->ctx, dec->as<double>(), 5);
     double h[5];
     SRB_CUDA(cudaMemcpyAsync(h, dec->p, sizeof(h), cudaMemcpyDeviceToHost, s));
     SRB_CUDA(cudaStreamSynchronize(s));
@@ -501,12 +501,14 @@ static void launch_fused(srb_mat *m, const FusedParams &p, bool write, unsigned 
 #undef SRB_FUSED_GO
 }
 
-// Apply the pending transforms; when want_moments, also produce the per-minor-line moments of the result.
-void materialize(srb_mat *m, bool want_moments) {
+// Apply the pending transforms; when want_moments, also produce the per-minor-line moments of the result — summed over
+// the ranks of a row-sharded CSR unless local_only (chunk moments of the backed / out-of-core drivers).
+void materialize(srb_mat *m, bool want_moments, bool local_only) {
     srb_ctx *c = m->ctx;
     cudaStream_t s = c->stream;
     const bool pending = m->has_pending();
-    if (!pending && (!want_moments || m->minor.valid)) return;
+    const bool reduce = !local_only && c->nranks > 1 && m->format == SRB_CSR;
+    if (!pending && (!want_moments || (m->minor.valid && m->minor.reduced == reduce))) return;
     Structure &st = *m->st;
     const uint64_t M = st.nminor, N = st.nmajor, nnz = st.nnz;
 
@@ -525,7 +527,7 @@ void materialize(srb_mat *m, bool want_moments) {
             bound = m->absmax_all;
         }
         Buf dec;
-        exact = m->major.valid && exact_path_ok(m, bound, pending, pending && m->pend_log1p, out_dtype, dec);
+        exact = m->major.valid && exact_path_ok(m, bound, pending, pending && m->pend_log1p, out_dtype, dec, reduce);
         if (exact) bound = dec;
     }
 
@@ -579,7 +581,7 @@ void materialize(srb_mat *m, bool want_moments) {
         mm.cnt = dev_alloc(s, sizeof(double) * (M ? M : 1));
         mm.sum = dev_alloc(s, sizeof(double) * (M ? M : 1));
         mm.sq = dev_alloc(s, sizeof(double) * (M ? M : 1));
-        if (c->nranks > 1 && m->format == SRB_CSR) {
+        if (reduce) {
             StageTimer t(c, ST_ALLREDUCE);
             allreduce_u64_sum(c, mm.acc->as<uint64_t>(), 6 * M);
             mm.reduced = true;
@@ -616,7 +618,7 @@ void materialize(srb_mat *m, bool want_moments) {
                 else
                     SRB_LAUNCH((moments_general_kernel<double>), grid, 256, 0, s, off, idx, new_values->as<double>(), N, mm.cnt->as<double>(), mm.sum->as<double>(), mm.sq->as<double>());
             }
-            if (c->nranks > 1 && m->format == SRB_CSR) {
+            if (reduce) {
                 StageTimer t(c, ST_ALLREDUCE);
                 allreduce_f64_sum(c, mm.cnt->as<double>(), M);
                 allreduce_f64_sum(c, mm.sum->as<double>(), M);
@@ -640,9 +642,10 @@ void materialize(srb_mat *m, bool want_moments) {
     if (want_moments) m->minor = mm;
 }
 
-void ensure_minor_moments(srb_mat *m) {
-    if (m->minor.valid && !m->has_pending()) return;
-    materialize(m, true);
+void ensure_minor_moments(srb_mat *m, bool local_only) {
+    const bool reduce = !local_only && m->ctx->nranks > 1 && m->format == SRB_CSR;
+    if (m->minor.valid && !m->has_pending() && m->minor.reduced == reduce) return;
+    materialize(m, true, local_only);  // a cache of the other flavour (local vs reduced) is recomputed, never reused
 }
 
 void minor_variance_from_moments(srb_mat *m, double *d_out, bool sqrt_it) {

@@ -501,7 +501,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
 // =====================================================================================================================
 struct srb_pca_stream {
     srb_ctx *ctx = nullptr;
-    uint64_t M = 0, n_sel = 0, k = 0, rows_seen = 0;
+    uint64_t M = 0, n_sel = 0, k = 0, rows_seen = 0, ncells_total = 0;
     double n_cells = 0.0;
     bool center = true, scale = true, fitted = false;
     int gram_mode = 0;
@@ -532,6 +532,7 @@ static void stream_densify(srb_pca_stream *ps, srb_mat *m, Buf &Xh, Buf &Xl) {
 
 static void stream_check_chunk(const srb_pca_stream *ps, const srb_mat *m) {
     SRB_REQUIRE(ps && m && m->ctx && m->st, SRB_ERR_INVALID_ARG, "null handle");
+    SRB_REQUIRE(ctx_alive(ps->ctx), SRB_ERR_INVALID_ARG, "the PCA stream outlived its context");
     SRB_REQUIRE(m->ctx == ps->ctx, SRB_ERR_INVALID_ARG, "chunk and PCA stream belong to different contexts");
     SRB_REQUIRE(m->format == SRB_CSR, SRB_ERR_UNSUPPORTED, "out-of-core PCA takes CSR row chunks");
     SRB_REQUIRE(m->ncols == ps->M, SRB_ERR_INVALID_ARG, "chunk has a different number of genes");
@@ -560,7 +561,7 @@ int32_t srb_pca_stream_begin(srb_ctx *ctx, uint64_t ncols, uint64_t ncells_total
         h[i] = (uint32_t)col_sel[i];
     }
     std::unique_ptr<srb_pca_stream> ps(new srb_pca_stream());
-    ps->ctx = ctx, ps->M = ncols, ps->n_sel = n_sel, ps->k = k, ps->n_cells = (double)ncells_total;
+    ps->ctx = ctx, ps->M = ncols, ps->n_sel = n_sel, ps->k = k, ps->n_cells = (double)ncells_total, ps->ncells_total = ncells_total;
     ps->center = center != 0, ps->scale = scale != 0, ps->gram_mode = gram_mode;
     const uint32_t dpad = ps->dpad = (uint32_t)((n_sel + 255) / 256 * 256);
     ps->kpad = (uint32_t)((k + 63) / 64 * 64);
@@ -632,6 +633,20 @@ int32_t srb_pca_stream_fit(srb_pca_stream *ps, double *components, double *expla
     cudaStream_t s = c->stream;
     const uint64_t n_sel = ps->n_sel, k = ps->k;
     const uint32_t dpad = ps->dpad, kpad = ps->kpad;
+    {
+        // every cell must have been pushed exactly once (over all ranks): the diagonal of C comes from the caller's global
+        // moments, the off-diagonals from the pushed chunks, and the two must describe the same cells
+        uint64_t seen = ps->rows_seen;
+        if (c->nranks > 1) {
+            Buf d_seen = dev_alloc(s, 8);
+            SRB_CUDA(cudaMemcpyAsync(d_seen->p, &seen, 8, cudaMemcpyHostToDevice, s));
+            allreduce_u64_sum(c, d_seen->as<uint64_t>(), 1);
+            SRB_CUDA(cudaMemcpyAsync(&seen, d_seen->p, 8, cudaMemcpyDeviceToHost, s));
+            SRB_CUDA(cudaStreamSynchronize(s));
+        }
+        SRB_REQUIRE(seen == ps->ncells_total, SRB_ERR_INVALID_ARG,
+                    "srb_pca_stream_fit: " + std::to_string(seen) + " cells were pushed but the stream was opened for " + std::to_string(ps->ncells_total));
+    }
     if (c->nranks > 1) allreduce_f64_sum(c, ps->G->as<double>(), (size_t)dpad * dpad);  // ranks hold disjoint chunks
     Buf C = dev_alloc(s, 8 * n_sel * n_sel), evals = dev_alloc(s, 8 * n_sel), tr = dev_alloc(s, 8);
     ps->comps = dev_alloc(s, 8 * n_sel * k), ps->W = dev_zeros(s, 8 * (size_t)dpad * kpad), ps->evr = dev_alloc(s, 8 * k);
@@ -682,8 +697,10 @@ int32_t srb_pca_stream_transform(srb_pca_stream *ps, srb_mat *chunk, double *sco
 int32_t srb_pca_stream_free(srb_pca_stream *ps) {
     SRB_API_BEGIN
     if (ps) {
-        cudaSetDevice(ps->ctx->device);
-        cudaStreamSynchronize(ps->ctx->stream);
+        if (ctx_alive(ps->ctx)) {
+            cudaSetDevice(ps->ctx->device);
+            cudaStreamSynchronize(ps->ctx->stream);
+        }
         delete ps;
     }
     SRB_API_END

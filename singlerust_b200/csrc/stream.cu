@@ -114,9 +114,8 @@ int32_t srb_stream_push(srb_stream *st, uint64_t nmajor_chunk, uint64_t nnz, con
                    st->r_off->as<int64_t>() + st->major_pos, nmajor_chunk + 1, (int64_t)st->nnz_pos);
         st->nnz_pos += nnz;
     }
-    const int saved_ranks = c->nranks;
-    c->nranks = 1;  // chunk moments are local; the caller reduces across ranks at the end if it shards chunks
-    try {
+    {
+        // chunk moments are local (never reduced over ranks); the caller reduces at the end if it shards chunks
         if (!st->stats) {
             // residency only
         } else if (nmajor_chunk) {
@@ -125,18 +124,14 @@ int32_t srb_stream_push(srb_stream *st, uint64_t nmajor_chunk, uint64_t nnz, con
             SRB_CUDA(cudaMemcpyAsync(st->major_sum->as<double>() + st->major_pos, chunk->major.sum->p, 8 * nmajor_chunk, cudaMemcpyDeviceToDevice, s));
             major_variance(chunk, st->major_var->as<double>() + st->major_pos);
         }
-        if (st->stats) ensure_minor_moments(chunk);
+        if (st->stats) ensure_minor_moments(chunk, /*local_only=*/true);
         const uint64_t M = st->nminor;
         if (st->stats && M) {
             SRB_LAUNCH(axpy1_kernel, nblk(M), 256, 0, s, st->minor_cnt->as<double>(), chunk->minor.cnt->as<double>(), M);
             SRB_LAUNCH(axpy1_kernel, nblk(M), 256, 0, s, st->minor_sum->as<double>(), chunk->minor.sum->as<double>(), M);
             SRB_LAUNCH(axpy1_kernel, nblk(M), 256, 0, s, st->minor_sq->as<double>(), chunk->minor.sq->as<double>(), M);
         }
-    } catch (...) {
-        c->nranks = saved_ranks;
-        throw;
     }
-    c->nranks = saved_ranks;
     st->major_pos += nmajor_chunk;
     SRB_CUDA(cudaStreamSynchronize(s));  // host arrays are only borrowed for the duration of the call
     SRB_API_END

@@ -30,13 +30,14 @@ __global__ void narrow_index_kernel(const SRC *__restrict__ src, uint32_t *__res
     }
     if (bad) atomicOr(flags, 1u);
 }
-// canonical form check: offsets monotone, indices strictly increasing within a line. flags[1] |= 1 otherwise
+// canonical form check: offsets start at 0 and are monotone, indices strictly increasing within a line. flags[1] |= 1 otherwise
 __global__ void canonical_check_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx, uint64_t nmajor,
                                        uint64_t nnz, uint32_t *__restrict__ flags) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     uint32_t bad = 0;
+    if (warp == 0 && off[0] != 0) bad = 1;  // entries before offsets[0] would belong to no line (nalgebra-sparse rejects it)
     for (uint64_t r = warp; r < nmajor; r += nwarps) {
         const int64_t a = off[r], b = off[r + 1];
         if (a > b || a < 0 || (uint64_t)b > nnz) { bad = 1; continue; }

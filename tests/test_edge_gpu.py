@@ -203,3 +203,55 @@ def test_line_lengths_around_the_warp_and_batch_boundaries(ffi, ctx):
     close(m.download()[2], ol.values, rtol=6e-7)
     close_compact_variance(m.variance(ffi.COLUMN), ol, O.COLUMN)
     close_compact_variance(m.variance(ffi.ROW), ol, O.ROW)
+
+
+def test_handles_may_outlive_their_context(ffi):
+    """A garbage-collected host frees handles in any order: a matrix freed after srb_ctx_destroy must neither crash nor
+    leave a CUDA error behind for the next call (round-1 bug: 'invalid device ordinal' in an unrelated upload)."""
+    a = random_csr(np.random.default_rng(3), 50, 20, 0.3)
+    c1 = ffi.Context(0)
+    m = ffi.DeviceMatrix.from_scipy(c1, a)
+    m2 = m.clone()
+    c1.close()
+    with pytest.raises(ffi.SrbError) as e:   # using it is an error, not a crash
+        m.sum(ffi.ROW)
+    assert e.value.code == -1
+    m.free(), m2.free()
+    c2 = ffi.Context(0)
+    try:
+        w = ffi.DeviceMatrix.from_scipy(c2, a)   # would have reported the stale error
+        np.testing.assert_array_equal(w.sum(ffi.ROW), O.sum_(O.Compressed.from_scipy(a), O.ROW))
+        w.free()
+    finally:
+        c2.close()
+
+
+def test_offsets_must_start_at_zero(ffi, ctx):
+    """offsets[0] = p > 0 leaves p entries that belong to no line; nalgebra-sparse rejects it, so does the upload."""
+    a = random_csr(np.random.default_rng(4), 30, 12, 0.4)
+    off = a.indptr.astype(np.uint64).copy()
+    off[0] = 2
+    for mode in (ffi.UPLOAD_DEVICE_NARROW, ffi.UPLOAD_HOST_PACK, ffi.UPLOAD_HOST_PACK_DELTA):
+        ctx.set_upload_mode(mode)
+        try:
+            with pytest.raises(ffi.SrbError) as e:
+                ffi.DeviceMatrix.upload(ctx, ffi.CSR, 30, 12, off, a.indices.astype(np.uint64), a.data, nnz=a.nnz)
+            assert e.value.code in (-1, -8), e.value   # INVALID_ARG or UNSUPPORTED (non-canonical)
+        finally:
+            ctx.set_upload_mode(ffi.UPLOAD_AUTO)
+
+
+def test_pca_stream_fit_requires_every_cell(ffi, ctx):
+    """srb_pca_stream_fit refuses a stream that has not seen exactly ncells_total cells."""
+    rng = np.random.default_rng(5)
+    a = random_csr(rng, 400, 60, 0.3)
+    m = ffi.DeviceMatrix.from_scipy(ctx, a)
+    cnt, s, q = m.gene_moments()
+    sel = np.arange(20, dtype=np.uint64)
+    ps = ffi.PcaStream(ctx, 60, 800, s, q, sel, 3)   # announces 800 cells, pushes 400
+    ps.push_gram(m)
+    with pytest.raises(ffi.SrbError) as e:
+        ps.fit()
+    assert e.value.code == -1
+    ps.free()
+    m.free()

@@ -11,11 +11,7 @@ from oracle import oracle as O
 from oracle import pca_oracle as P
 from tests._util import sign_align
 
-# This path was written after round 1's GPU budget was spent: it has compiled and its host side is CPU-tested, but it
-# has never run on a GPU. tools/r2_first_call.sh sets SRB_TEST_PENDING=1 for its first run; once green the gate goes.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SRB_TEST_PENDING") != "1",
-                                 reason="first GPU run pending (round 2): set SRB_TEST_PENDING=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

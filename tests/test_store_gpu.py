@@ -8,11 +8,7 @@ import pytest
 from oracle import oracle as O
 from tests._util import random_csr, sign_align
 
-# Written after round 1's last GPU call: the code path under test has run on the GPU (tools/chfsi_probe.py, the backed
-# pipeline tests), this test file has not. tools/r2_first_call.sh sets SRB_TEST_PENDING=1 for its first run.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("SRB_TEST_PENDING") != "1",
-                                 reason="first GPU run pending (round 2): set SRB_TEST_PENDING=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("fmt", ["csr", "csc"])

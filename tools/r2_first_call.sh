@@ -7,7 +7,7 @@
 mkdir -p gpurun_out
 S=gpurun_out/r2_summary.txt
 : > $S
-SRB_TEST_PENDING=1 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/r2_tests.log 2>&1; echo "pytest -m gpu rc=$? $(tail -1 gpurun_out/r2_tests.log)" >> $S
+SRB_TEST_PENDING=1 timeout 600 python -m pytest tests -m gpu -q --durations=30 --timeout=180 > gpurun_out/r2_tests.log 2>&1; echo "pytest -m gpu rc=$? $(tail -1 gpurun_out/r2_tests.log)" >> $S
 grep -E "FAILED|ERROR" gpurun_out/r2_tests.log | head -20 >> $S
 rm -f gpurun_out/e2e_ab.jsonl
 AB_REPS=2 timeout 300 python tools/e2e_ab.py > gpurun_out/r2_e2e_ab.log 2>&1; echo "e2e_ab rc=$?" >> $S
