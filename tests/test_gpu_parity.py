@@ -398,6 +398,52 @@ def test_pca_tensor_core_gram_matches_fp64_and_oracle(ffi, ctx, n, m, n_top, k):
     assert good[:3].all()
 
 
+def test_config_L_slice_against_the_oracle(ffi, ctx):
+    """The bench configuration itself — 30 k genes, HVG 2000, 50 PCs, the default K8 solver (ChFSI at d >= 1024) and the
+    tcgen05 Gram / scores — on the first 16 384 cells of the L matrix (seed 0x5EED0002), against the oracle's SVD PCA.
+    The spectrum of this synthetic block is flat (no cell programmes), so individual loadings are only compared where
+    the eigengap allows; every component is additionally checked through its eigen-residual on the ORACLE's matrix,
+    which does not depend on the gaps: || Z^T Z v - lambda v || <= 1e-5 lambda."""
+    from singlerust_b200 import synth
+    n, m, d, k = 16_384, 30_000, 2_000, 50
+    thr, amp = synth.gene_tables(m, seed=0x5EED0002, mean_density=0.05)
+    mat = ffi.DeviceMatrix.synth(ctx, 0x5EED0002, n, m, thr, amp)
+    cpu = O.synth_csr(0x5EED0002, n, m, thr, amp)
+    off, idx, val = mat.download(values="f32")
+    assert np.array_equal(off, cpu.offsets) and np.array_equal(idx, cpu.indices) and np.array_equal(val, cpu.values)
+    res = mat.pipeline_normalize_hvg_pca(1e4, d, k)
+    assert ctx.last_eig()["solver"] in ("chfsi", "chfsi->syevd")
+    # HVG list: bit-exact against the oracle run on the device's stored (f32) values, set-equal against the f64 oracle
+    off, idx, val = mat.download()
+    ol = O.Compressed("csr", n, m, off, idx, val)
+    np.testing.assert_array_equal(res["selection"], O.select_hvg(O.variance(ol, O.COLUMN), d))
+    ol64 = O.log1p(O.normalize_total(cpu, 1e4, O.ROW))
+    want_sel = O.select_hvg(O.variance(ol64, O.COLUMN), d)
+    assert len(set(res["selection"].tolist()) ^ set(want_sel.tolist())) <= 2   # f32 storage may swap a near-tie at the cut
+    want = P.pca_pipeline(ol, d, k, selection=res["selection"])
+    np.testing.assert_allclose(res["explained_variance_ratio"], want["explained_variance_ratio"], rtol=RTOL)
+    V = res["components"]
+    np.testing.assert_allclose(V.T @ V, np.eye(k), atol=1e-9)
+    # gap-independent: residual of every returned pair on the oracle's standardised block
+    dense = O.densify_selected(ol, np.arange(n, dtype=np.uint64), res["selection"])
+    Z = (dense - want["mean"]) / want["std"]
+    lam = want["eigenvalues"][:k] * (n - 1)
+    R = Z.T @ (Z @ V) - V * lam
+    rel = np.linalg.norm(R, axis=0) / lam
+    print("eigen-residuals on the oracle matrix: max %.2e" % rel.max())
+    assert rel.max() <= RTOL
+    scores = sign_align(res["scores"], Z @ sign_align(V, want["components"]))
+    good = well_separated(want["eigenvalues"], k)
+    comps = sign_align(V, want["components"])
+    for j in np.nonzero(good)[0]:
+        assert np.max(np.abs(comps[:, j] - want["components"][:, j])) <= RTOL, j
+    # scores = Z V for the RETURNED loadings (exact relation, no gap involved)
+    ZV = Z @ V
+    np.testing.assert_allclose(res["scores"], ZV, rtol=0, atol=10 * RTOL * np.abs(ZV).max())
+    del scores
+    mat.free()
+
+
 def test_full_size_config_L_properties(ffi, ctx):
     """BASELINE.json configs[1]/[2] at FULL size (1M cells x 30k genes, ~1.5 G nnz) through size-independent properties:
     count conservation, the reference's normalisation invariant, and the PCA identities
