@@ -35,6 +35,7 @@ extern "C" {
     pub fn srb_ctx_last_eig(ctx: *mut srb_ctx, solver: *mut i32, block_products: *mut i32, outer_iterations: *mut i32,
                             max_residual: *mut f64) -> i32;
     pub fn srb_ctx_last_upload(ctx: *mut srb_ctx, h2d_bytes: *mut u64, host_packed: *mut i32) -> i32;
+    pub fn srb_ctx_last_upload_chunks(ctx: *mut srb_ctx, chunks: *mut i32, index_chunks_packed: *mut i32, value_chunks_packed: *mut i32) -> i32;
     pub fn srb_ctx_synchronize(ctx: *mut srb_ctx) -> i32;
     pub fn srb_ctx_stream(ctx: *mut srb_ctx) -> *mut c_void;
     pub fn srb_last_stage_ms(ctx: *mut srb_ctx, out_ms: *mut f32, n: i32) -> i32;

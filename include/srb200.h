@@ -70,12 +70,16 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *   HOST_PACK_DELTA  HOST_PACK with the sorted indices of each line delta-coded to ONE byte per entry (gap to the previous
  *                  index; gaps >= 255, line starts beyond 254 and non-canonical pairs escape to a side list), rebuilt
  *                  exactly on the device. Host coder tested on the CPU; device decode not yet measured (round 2).
- *   AUTO           HOST_PACK when the array has >= 2^20 entries and this context may use >= 6 host threads
- *                  (min(hardware threads, 16, SRB_UPLOAD_THREADS) / ranks on the node), else DEVICE_NARROW
- * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values | adaptive | delta) overrides it. */
+ *   BALANCED       every 4 M-entry chunk is either packed on the host (indices: DELTA codes, or HOST_PACK narrowing when the
+ *                  offsets cannot be trusted; f32 counts: u8 / u16 where lossless) or sent raw and narrowed on the device —
+ *                  packed exactly when the copies already queued on the link take at least as long as packing the chunk
+ *                  (measured, running estimate), so host and link stay busy for any number of host threads per rank
+ *   AUTO           BALANCED for arrays of >= 2^20 entries, else DEVICE_NARROW
+ * Process default: AUTO; environment SRB_UPLOAD_PACK (0 | 1 | auto | values | adaptive | delta | balanced) overrides it;
+ * SRB_LINK_GBS (default 50) is the link rate BALANCED assumes when it converts queued bytes into time. */
 typedef enum srb_upload_mode {
     SRB_UPLOAD_DEVICE_NARROW = 0, SRB_UPLOAD_HOST_PACK = 1, SRB_UPLOAD_AUTO = 2, SRB_UPLOAD_HOST_PACK_VALUES = 3,
-    SRB_UPLOAD_HOST_PACK_ADAPTIVE = 4, SRB_UPLOAD_HOST_PACK_DELTA = 5
+    SRB_UPLOAD_HOST_PACK_ADAPTIVE = 4, SRB_UPLOAD_HOST_PACK_DELTA = 5, SRB_UPLOAD_BALANCED = 6
 } srb_upload_mode;
 
 /* K8, the eigensolver behind srb_pca (top-k eigenpairs of the n_sel x n_sel correlation matrix):
@@ -126,6 +130,8 @@ int32_t srb_ctx_set_eig_mode(srb_ctx *ctx, int32_t mode /* srb_eig_mode */);
 int32_t srb_ctx_last_eig(srb_ctx *ctx, int32_t *solver, int32_t *block_products, int32_t *outer_iterations, double *max_residual);
 /* what the last srb_mat_upload on this ctx moved over the link: bytes, and whether the index array was host-packed */
 int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_packed);
+/* BALANCED upload only: chunks of the last upload, and how many of them had their indices / values packed on the host */
+int32_t srb_ctx_last_upload_chunks(srb_ctx *ctx, int32_t *chunks, int32_t *index_chunks_packed, int32_t *value_chunks_packed);
 int32_t srb_ctx_synchronize(srb_ctx *ctx);
 /* the cudaStream_t all work of this ctx is enqueued on (for CUDA-event timing by the caller) */
 void *srb_ctx_stream(srb_ctx *ctx);

@@ -17,6 +17,7 @@ GRAM_TENSOR, GRAM_FP64 = 0, 1
 EIG_SYEVD, EIG_CHFSI = 0, 1
 UPLOAD_DEVICE_NARROW, UPLOAD_HOST_PACK, UPLOAD_AUTO, UPLOAD_HOST_PACK_VALUES, UPLOAD_HOST_PACK_ADAPTIVE = 0, 1, 2, 3, 4
 UPLOAD_HOST_PACK_DELTA = 5
+UPLOAD_BALANCED = 6
 
 DTYPES = {np.dtype(np.int8): 0, np.dtype(np.int16): 1, np.dtype(np.int32): 2, np.dtype(np.int64): 3,
           np.dtype(np.uint8): 4, np.dtype(np.uint16): 5, np.dtype(np.uint32): 6, np.dtype(np.uint64): 7,
@@ -57,6 +58,7 @@ def lib() -> C.CDLL:
             "srb_ctx_set_upload_mode": [vp, i32],
             "srb_host_pack_indices": [vp, i32, u64, vp, i32, u64, i32, C.POINTER(i32)],
             "srb_ctx_last_upload": [vp, C.POINTER(u64), C.POINTER(i32)],
+            "srb_ctx_last_upload_chunks": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
             "srb_ctx_set_eig_mode": [vp, i32],
             "srb_ctx_last_eig": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(f64)],
             "srb_host_pack_values_f32": [vp, u64, vp, i32, i32, C.POINTER(i32)],
@@ -203,6 +205,12 @@ class Context:
         b, p = C.c_uint64(0), C.c_int32(0)
         check(lib().srb_ctx_last_upload(self._h, C.byref(b), C.byref(p)))
         return int(b.value), bool(p.value)
+
+    def last_upload_chunks(self):
+        """BALANCED upload: (chunks, chunks whose indices were host-packed, chunks whose values were host-packed)"""
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(lib().srb_ctx_last_upload_chunks(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def synchronize(self):
         check(lib().srb_ctx_synchronize(self._h))

@@ -6,6 +6,7 @@
 #include <cusolverDn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -60,16 +61,6 @@ __global__ void fill_random_kernel(double *__restrict__ a, uint64_t n, uint64_t 
         a[i] = (double)(int64_t)z * (1.0 / 9223372036854775808.0);  // uniform in (-1, 1)
     }
 }
-// v = w / *nrm ; *flag |= 1 when the norm has collapsed (Krylov breakdown) or is not finite
-__global__ void scale_by_inv_norm_kernel(const double *__restrict__ w, double *__restrict__ v, uint32_t n, const double *nrm,
-                                         const double *ref, uint32_t *flag) {
-    const double x = *nrm;
-    const bool bad = !(x > 1e-13 * fabs(*ref)) || !isfinite(x);
-    const double inv = bad ? 0.0 : 1.0 / x;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = w[i] * inv;
-    if (bad && i == 0) atomicOr(flag, 1u);
-}
 // dst = src - c I  (both d x d, column-major)
 __global__ void shift_copy_kernel(const double *__restrict__ src, double *__restrict__ dst, uint32_t d, double c) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,6 +97,109 @@ __global__ void residual_norms_kernel(const double *__restrict__ cw, const doubl
         v = warp_sum(v);
         if (threadIdx.x == 0) out[j] = sqrt(v);
     }
+}
+
+// ---- Krylov bounds: hand-written Lanczos step (replaces ~7 cuBLAS launches per step) -------------------------------
+// w = C v for a SYMMETRIC column-major C: w[i] = <C[:, i], v>, so every warp streams one contiguous column (coalesced
+// 256-byte warp loads, C stays in L2 between steps: 32 MB at d = 2000). The product is written twice: into the next basis
+// slot (to be orthogonalised) and into CV[:, j] (kept for the projected matrix H = V^T C V).
+__global__ void __launch_bounds__(256) symv_cols_kernel(const double *__restrict__ C, const double *__restrict__ v, uint32_t d,
+                                                        double *__restrict__ w, double *__restrict__ cv) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = gridDim.x * 8;
+    for (uint32_t col = warp; col < d; col += nwarps) {
+        const double *c = C + (size_t)col * d;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        uint32_t i = lane;
+        for (; i + 96 < d; i += 128) a0 += c[i] * v[i], a1 += c[i + 32] * v[i + 32], a2 += c[i + 64] * v[i + 64], a3 += c[i + 96] * v[i + 96];
+        for (; i < d; i += 32) a0 += c[i] * v[i];
+        const double acc = warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) w[col] = acc, cv[col] = acc;
+    }
+}
+__device__ __forceinline__ double block_sum_1024(double v, double *sh) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = (threadIdx.x & 31) < (blockDim.x >> 5) ? sh[threadIdx.x & 31] : 0.0;
+    return warp_sum(t);
+}
+// v0 = normalised splitmix64 noise (one CTA)
+__global__ void __launch_bounds__(1024) lanczos_init_kernel(double *__restrict__ v, uint32_t d, uint64_t seed) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
+        uint64_t z = ((uint64_t)i + 1) * 0x9E3779B97F4A7C15ull + seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const double x = (double)(int64_t)z * (1.0 / 9223372036854775808.0);
+        v[i] = x;
+        acc += x * x;
+    }
+    const double inv = rsqrt(block_sum_1024(acc, sh));
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) v[i] *= inv;
+}
+// One CTA: w = V[:, j+1] (holding C v_j) is orthogonalised twice against V[:, 0..j] (CGS2), beta_j = ||w|| goes to
+// sc[2 + j], v_{j+1} = w / beta_j. sc[1] = ||C v_0|| is the reference magnitude of the breakdown test (flag[0]).
+// Dynamic shared memory: w (d doubles) + the coefficients h (j + 1 doubles).
+__global__ void __launch_bounds__(1024) lanczos_orth_kernel(double *__restrict__ V, uint32_t d, int j, double *__restrict__ sc,
+                                                            uint32_t *__restrict__ flag) {
+    extern __shared__ double lz[];
+    __shared__ double sh[32];
+    double *w = lz, *h = lz + d;
+    double *wg = V + (size_t)(j + 1) * d;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    double nrm0 = 0.0;
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
+        const double x = wg[i];
+        w[i] = x;
+        nrm0 += x * x;
+    }
+    nrm0 = block_sum_1024(nrm0, sh);
+    if (j == 0 && threadIdx.x == 0) sc[1] = sqrt(nrm0);
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = (int)warp; c <= j; c += (int)nw) {  // h = V^T w: one warp per basis column
+            const double *vc = V + (size_t)c * d;
+            double a = 0.0;
+            for (uint32_t i = lane; i < d; i += 32) a += vc[i] * w[i];
+            a = warp_sum(a);
+            if (lane == 0) h[c] = a;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {  // w -= V h
+            double x = w[i];
+            for (int c = 0; c <= j; ++c) x -= V[(size_t)c * d + i] * h[c];
+            w[i] = x;
+        }
+        __syncthreads();
+    }
+    double nrm = 0.0;
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) nrm += w[i] * w[i];
+    nrm = sqrt(block_sum_1024(nrm, sh));
+    const double ref = j == 0 ? sqrt(nrm0) : sc[1];
+    const bool bad = !(nrm > 1e-13 * fabs(ref)) || !isfinite(nrm);
+    const double inv = bad ? 0.0 : 1.0 / nrm;
+    for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) wg[i] = w[i] * inv;
+    if (threadIdx.x == 0) {
+        sc[2 + j] = nrm;
+        if (bad) atomicOr(flag, 1u);
+    }
+}
+// H[a][b] = <V[:, a], CV[:, b]>  (L x L, one CTA per entry)
+__global__ void __launch_bounds__(128) krylov_project_kernel(const double *__restrict__ V, const double *__restrict__ CV, uint32_t d, int L,
+                                                             double *__restrict__ H) {
+    const int a = blockIdx.x % L, b = blockIdx.x / L;
+    const double *va = V + (size_t)a * d, *cb = CV + (size_t)b * d;
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < d; i += 128) acc += va[i] * cb[i];
+    __shared__ double sh[4];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) H[(size_t)a * L + b] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
 }
 
 // cyclic Jacobi on a small symmetric matrix (row-major n x n, destroyed); eigenvalues ascending, vecs[i * n + j] =
@@ -161,6 +255,30 @@ struct ChfsiStats {
     double max_residual = 0.0;
 };
 
+// SRB_EIG_TRACE=1: wall-clock per phase (synchronising — for probes only, never in a timed run)
+struct PhaseTrace {
+    bool on;
+    cudaStream_t s;
+    double t0, acc[5] = {0, 0, 0, 0, 0};  // krylov, filter, cholqr, rayleigh-ritz, other
+    static double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    explicit PhaseTrace(cudaStream_t st) : s(st) {
+        const char *e = getenv("SRB_EIG_TRACE");
+        on = e && e[0] == '1';
+        if (on) cudaStreamSynchronize(s), t0 = now();
+    }
+    void mark(int phase) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const double t = now();
+        acc[phase] += t - t0, t0 = t;
+    }
+    void report(const ChfsiStats &st) const {
+        if (on)
+            fprintf(stderr, "[srb] chfsi phases (ms): krylov %.3f filter %.3f cholqr %.3f rayleigh-ritz %.3f other %.3f | products %d cholqr %d outer %d\n",
+                    acc[0], acc[1], acc[2], acc[3], acc[4], st.block_products, st.cholqr, st.outer);
+    }
+};
+
 // Leading k eigenpairs of the symmetric d x d matrix d_C (column-major, untouched unless true is returned): on success
 // columns 0..k-1 of d_C hold the eigenvectors of the k largest eigenvalues in ASCENDING order and d_evals[0..k-1] the values.
 static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, cudaStream_t es, double *d_C, uint32_t d, uint32_t k,
@@ -190,10 +308,10 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
     ChfsiStats st;
     // ---- workspace ----
     Buf bV = dev_alloc(es, 8 * (size_t)d * (L + 1)), bCV = dev_alloc(es, 8 * (size_t)d * L), bH = dev_alloc(es, 8 * (size_t)L * L);
-    Buf bh = dev_alloc(es, 8 * (L + 1)), bsc = dev_zeros(es, 8 * (L + 4)), bflag = dev_zeros(es, 4 * 64);
+    Buf bsc = dev_zeros(es, 8 * (L + 4)), bflag = dev_zeros(es, 4 * 64);
     Buf bCs = dev_alloc(es, 8 * dd), bY0 = dev_alloc(es, 8 * db), bY1 = dev_alloc(es, 8 * db), bW = dev_alloc(es, 8 * db);
     Buf bG = dev_alloc(es, 8 * (size_t)b * b), bth = dev_alloc(es, 8 * b), bres = dev_alloc(es, 8 * k), bCW = dev_alloc(es, 8 * (size_t)d * k);
-    double *V = bV->as<double>(), *CV = bCV->as<double>(), *H = bH->as<double>(), *hvec = bh->as<double>(), *sc = bsc->as<double>();
+    double *V = bV->as<double>(), *CV = bCV->as<double>(), *H = bH->as<double>(), *sc = bsc->as<double>();
     uint32_t *flag = bflag->as<uint32_t>();  // [0] Krylov breakdown, [1 + i] LAPACK infos
     int *infos = reinterpret_cast<int *>(flag + 1);
     int n_info = 0;
@@ -205,39 +323,25 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
     Buf bwork = dev_alloc(es, 8 * (size_t)std::max(std::max(lw_potrf, lw_syevd), 1));
     double *work = bwork->as<double>();
     SRB_CUBLAS(cublasSetStream(bl, es));
-    const unsigned gv = (d + 255) / 256;
+    PhaseTrace trace(es);
 
-    // ---- 1. Krylov bounds: v_{j+1} = normalise((I - V V^T)^2 C v_j) ----
-    SRB_LAUNCH(fill_random_kernel, 8, 256, 0, es, V, (uint64_t)d, 0x5EEDC0DEull);
-    SRB_CUBLAS(cublasSetPointerMode(bl, CUBLAS_POINTER_MODE_DEVICE));
-    SRB_CUBLAS(cublasDnrm2(bl, (int)d, V, 1, sc + 0));
-    SRB_LAUNCH(scale_by_inv_norm_kernel, gv, 256, 0, es, V, V, d, sc + 0, sc + 0, flag);
-    SRB_CUBLAS(cublasSetPointerMode(bl, CUBLAS_POINTER_MODE_HOST));
+    // ---- 1. Krylov bounds: v_{j+1} = normalise((I - V V^T)^2 C v_j), two own launches per step ----
+    if ((size_t)8 * (d + L + 1) > ctx->smem_optin) return false;  // w must fit one CTA's shared memory: syevd instead
+    const size_t lz_smem = 8 * ((size_t)d + L + 1);
+    SRB_CUDA(cudaFuncSetAttribute(lanczos_orth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem));
+    SRB_LAUNCH(lanczos_init_kernel, 1, 1024, 0, es, V, d, 0x5EEDC0DEull);
     for (int j = 0; j < L; ++j) {
-        double *vj = V + (size_t)j * d, *w = V + (size_t)(j + 1) * d;
-        SRB_CUBLAS(cublasDgemv(bl, CUBLAS_OP_N, (int)d, (int)d, &one, d_C, (int)d, vj, 1, &zero, w, 1));
-        if (j == 0) {  // reference magnitude for the breakdown test: ||C v_0||
-            SRB_CUBLAS(cublasSetPointerMode(bl, CUBLAS_POINTER_MODE_DEVICE));
-            SRB_CUBLAS(cublasDnrm2(bl, (int)d, w, 1, sc + 1));
-            SRB_CUBLAS(cublasSetPointerMode(bl, CUBLAS_POINTER_MODE_HOST));
-        }
-        for (int pass = 0; pass < 2; ++pass) {
-            SRB_CUBLAS(cublasDgemv(bl, CUBLAS_OP_T, (int)d, j + 1, &one, V, (int)d, w, 1, &zero, hvec, 1));
-            SRB_CUBLAS(cublasDgemv(bl, CUBLAS_OP_N, (int)d, j + 1, &minus1, V, (int)d, hvec, 1, &one, w, 1));
-        }
-        SRB_CUBLAS(cublasSetPointerMode(bl, CUBLAS_POINTER_MODE_DEVICE));
-        SRB_CUBLAS(cublasDnrm2(bl, (int)d, w, 1, sc + 2 + j));
-        SRB_CUBLAS(cublasSetPointerMode(bl, CUBLAS_POINTER_MODE_HOST));
-        SRB_LAUNCH(scale_by_inv_norm_kernel, gv, 256, 0, es, w, w, d, sc + 2 + j, sc + 1, flag);
+        SRB_LAUNCH(symv_cols_kernel, (d + 7) / 8, 256, 0, es, d_C, V + (size_t)j * d, d, V + (size_t)(j + 1) * d, CV + (size_t)j * d);
+        SRB_LAUNCH(lanczos_orth_kernel, 1, 1024, lz_smem, es, V, d, j, sc, flag);
     }
-    SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, L, (int)d, &one, d_C, (int)d, V, (int)d, &zero, CV, (int)d));
-    SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_T, CUBLAS_OP_N, L, L, (int)d, &one, V, (int)d, CV, (int)d, &zero, H, L));
+    SRB_LAUNCH(krylov_project_kernel, (unsigned)(L * L), 128, 0, es, V, CV, d, L, H);
     std::vector<double> hH((size_t)L * L), hsc(L + 4);
     uint32_t hflag0 = 0;
     SRB_CUDA(cudaMemcpyAsync(hH.data(), H, 8 * hH.size(), cudaMemcpyDeviceToHost, es));
     SRB_CUDA(cudaMemcpyAsync(hsc.data(), sc, 8 * hsc.size(), cudaMemcpyDeviceToHost, es));
     SRB_CUDA(cudaMemcpyAsync(&hflag0, flag, 4, cudaMemcpyDeviceToHost, es));
     SRB_CUDA(cudaStreamSynchronize(es));
+    trace.mark(0);
     if (hflag0) return false;
     for (double x : hH)
         if (!std::isfinite(x)) return false;
@@ -285,6 +389,7 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         if (n_info + 2 * rounds + 1 > 60) return false;
         // work budget: beyond ~400 block products the iteration would cost more than the syevd it replaces
         if (st.block_products + rounds * m > kMaxProducts) return false;
+        trace.mark(4);
         SRB_LAUNCH(shift_copy_kernel, (unsigned)((dd + 255) / 256), 256, 0, es, d_C, Cs, d, c);
         for (int r = 0; r < rounds; ++r) {
             // scaled Chebyshev recurrence (Zhou & Saad): Y_1 = (s1/e) Cs Y_0 ; Y_{i+1} = (2 s_{i+1}/e) Cs Y_i - s_i s_{i+1} Y_{i-1}
@@ -300,9 +405,11 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
             }
             st.block_products += m;
             if (Yc != Y) std::swap(Y, Yb);  // Y = filtered block, Yb = scratch
+            trace.mark(1);
             cholqr(Y);
             cholqr(Y);
             ++st.cholqr;
+            trace.mark(2);
         }
         // Rayleigh-Ritz
         SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)d, &one, d_C, (int)d, Y, (int)d, &zero, W, (int)d));
@@ -319,6 +426,7 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         SRB_CUDA(cudaMemcpyAsync(hres.data(), res, 8 * k, cudaMemcpyDeviceToHost, es));
         SRB_CUDA(cudaMemcpyAsync(hinfo.data(), infos, 4 * n_info, cudaMemcpyDeviceToHost, es));
         SRB_CUDA(cudaStreamSynchronize(es));
+        trace.mark(3);
         for (int i = 0; i < n_info; ++i)
             if (hinfo[i] != 0) return false;
         n_info = 0;
@@ -335,6 +443,7 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         if (!(cut > lo)) lo = cut - 0.05 * (up - cut);
     }
     ctx->last_eig_products = st.block_products, ctx->last_eig_outer = st.outer, ctx->last_eig_residual = st.max_residual;
+    trace.report(st);
     if (!converged) return false;
     SRB_CUDA(cudaMemcpyAsync(d_C, Y + (size_t)(b - k) * d, 8 * (size_t)d * k, cudaMemcpyDeviceToDevice, es));
     SRB_CUDA(cudaMemcpyAsync(d_evals, theta + (b - k), 8 * k, cudaMemcpyDeviceToDevice, es));
@@ -456,6 +565,14 @@ uint32_t sym_eig_desc(srb_ctx *ctx, double *d_C, uint32_t d, uint32_t topk, doub
     SRB_CUDA(cudaStreamWaitEvent(s, ctx->eig_out, 0));
     SRB_CUDA(cudaStreamSynchronize(es));
     SRB_REQUIRE(hinfo == 0, SRB_ERR_NAN, "syevd did not converge / illegal value (info=" + std::to_string(hinfo) + "): NaN in the correlation matrix?");
+    if (const char *dump = getenv("SRB_EIG_DUMP")) {  // probe: the full spectrum (ascending f64) for offline solver tuning
+        std::vector<double> ev(d);
+        SRB_CUDA(cudaMemcpy(ev.data(), d_evals, 8 * (size_t)d, cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(dump, "wb")) {
+            fwrite(ev.data(), 8, d, f);
+            fclose(f);
+        }
+    }
     return d;
 }
 

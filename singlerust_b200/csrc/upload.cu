@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <vector>
 
@@ -114,17 +115,18 @@ static int upload_pack_mode() {
         else if (!strcmp(e, "values")) v = SRB_UPLOAD_HOST_PACK_VALUES;
         else if (!strcmp(e, "adaptive")) v = SRB_UPLOAD_HOST_PACK_ADAPTIVE;
         else if (!strcmp(e, "delta")) v = SRB_UPLOAD_HOST_PACK_DELTA;
+        else if (!strcmp(e, "balanced")) v = SRB_UPLOAD_BALANCED;
         else v = atoi(e) != 0 ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
     }
     return v;
 }
 // host threads one context may use for packing: the ranks of a node share its cores
 static int upload_threads(const srb_ctx *c) { return std::max(1, host_pack_threads() / std::max(1, c->nranks)); }
-// AUTO: packing pays when the host narrows faster than the link moves the unpacked array (12 B per entry at ~55 GB/s =
-// 4.6 G entries/s; one host thread packs ~0.9 G entries/s), i.e. with >= 6 threads, and only for arrays worth a ring
+// AUTO: the balanced upload decides chunk by chunk from the measured packing time against the queued link work, whatever
+// the number of host threads per rank; arrays too small to be worth a staging ring are narrowed on the device
 static int effective_upload_mode(const srb_ctx *c, uint64_t nnz) {
     const int mode = c->upload_mode >= 0 ? c->upload_mode : upload_pack_mode();
-    if (mode == SRB_UPLOAD_AUTO) return (nnz >= (1ull << 20) && upload_threads(c) >= 6) ? SRB_UPLOAD_HOST_PACK : SRB_UPLOAD_DEVICE_NARROW;
+    if (mode == SRB_UPLOAD_AUTO) return nnz >= (1ull << 20) ? SRB_UPLOAD_BALANCED : SRB_UPLOAD_DEVICE_NARROW;
     return mode;
 }
 static bool host_is_pageable(const void *p) {
@@ -160,9 +162,12 @@ __global__ void unpack_values_kernel(const uint8_t *__restrict__ pk, float *__re
 }
 // HOST_PACK_DELTA: rebuild the u32 indices from the one-byte gap codes (host_pack.cpp). One warp per line: a segmented
 // inclusive scan in which an escape (code 255: the full index sits in the sorted side list) restarts the running sum.
+// raw_chunk (may be null): raw_chunk[i >> chunk_shift] != 0 marks a chunk of entries that travelled unpacked — out[i]
+// already holds their index (narrowed by its own kernel), which takes part in the scan as a restart value.
 __global__ void delta_decode_kernel(const uint8_t *__restrict__ code, const int64_t *__restrict__ off, uint64_t nmajor,
                                     const uint64_t *__restrict__ esc_pos, const uint32_t *__restrict__ esc_val, uint64_t n_esc,
-                                    uint64_t bound, uint32_t *__restrict__ out, uint32_t *__restrict__ flags) {
+                                    uint64_t bound, uint32_t *__restrict__ out, uint32_t *__restrict__ flags,
+                                    const uint8_t *__restrict__ raw_chunk, int chunk_shift) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -173,9 +178,10 @@ __global__ void delta_decode_kernel(const uint8_t *__restrict__ code, const int6
         for (int64_t base = a; base < b; base += 32) {
             const int64_t i = base + lane;
             const bool valid = i < b;
-            uint32_t v = valid ? code[i] : 0u;
-            int reset = 0;
-            if (valid && v == 255u) {  // binary search of the escape list for position i
+            const bool raw = valid && raw_chunk && raw_chunk[i >> chunk_shift];
+            uint32_t v = valid ? (raw ? out[i] : (uint32_t)code[i]) : 0u;
+            int reset = raw ? 1 : 0;
+            if (valid && !raw && v == 255u) {  // binary search of the escape list for position i
                 uint64_t lo = 0, hi = n_esc;
                 while (lo < hi) {
                     const uint64_t mid = (lo + hi) >> 1;
@@ -193,7 +199,7 @@ __global__ void delta_decode_kernel(const uint8_t *__restrict__ code, const int6
                 if (lane >= o && !reset) v += pv, reset = pr;
             }
             const uint32_t col = reset ? v : v + carry;
-            if (valid) {
+            if (valid && !raw) {
                 out[i] = col;
                 bad |= (uint32_t)((uint64_t)col >= bound);
             }
@@ -282,7 +288,8 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
             link += 12 * ne;
         }
         const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nmajor + 7) / 8, (uint64_t)c->sm_count * 16));
-        SRB_LAUNCH(delta_decode_kernel, g, 256, 0, s, dpk->as<uint8_t>(), d_offsets, nmajor, dpos->as<uint64_t>(), dval->as<uint32_t>(), ne, bound, d_idx, d_flags);
+        SRB_LAUNCH(delta_decode_kernel, g, 256, 0, s, dpk->as<uint8_t>(), d_offsets, nmajor, dpos->as<uint64_t>(), dval->as<uint32_t>(), ne, bound, d_idx, d_flags,
+                   (const uint8_t *)nullptr, 0);
         sync_needed = true;  // `esc` (pageable) and the escape buffers are done with
     } else if (pw == 2) {
         SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, n), 256, 0, s, dpk->as<uint16_t>(), d_idx, n, bound, d_flags);
@@ -301,6 +308,181 @@ static uint64_t upload_packed(srb_ctx *c, const void *indices, int width, uint64
     return link;
 }
 
+
+// ---- balanced upload (SRB_UPLOAD_BALANCED, what AUTO resolves to) ----------------------------------------------------
+// Every chunk of 4 M entries decides for itself how it crosses PCIe: packed on the host (indices: one-byte gap codes, or
+// 2 / 4-byte narrowing when the offsets cannot be trusted; f32 count values: u8 / u16 where lossless) or raw (the caller's
+// bytes as they are, narrowed on the device). Packing trades host time for link bytes, so a chunk is packed exactly when
+// the link still has at least that much work queued (bytes enqueued but not yet copied / the link rate >= the running
+// estimate of the packing time): with many cores per GPU everything is packed and the link carries 5 B per entry instead of
+// 12; with 2 threads per rank (8 ranks on a 16-core host) most chunks go raw and neither side waits for the other.
+// Index packing is decided first (it saves 7 link bytes per 8 host bytes read; value packing 3 per 4). Pageable caller
+// memory is always packed (staging it raw would cost the host more than coding it).
+static double link_rate_bytes_per_ms() {  // read per upload (not cached): tests steer the raw / packed mix with it
+    const char *e = getenv("SRB_LINK_GBS");
+    const double g = e ? atof(e) : 50.0;
+    return (g > 0.0 ? g : 50.0) * 1e6;
+}
+static double host_now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint64_t n, uint64_t bound, uint32_t *d_idx, uint32_t *d_flags,
+                                const void *values, size_t vsz, void *d_val, const void *offsets, uint64_t nmajor, const int64_t *d_offsets) {
+    c->last_upload_chunks = c->last_upload_idx_packed = c->last_upload_val_packed = 0;
+    if (n == 0) return 0;
+    cudaStream_t s = c->stream;
+    const int nthreads = upload_threads(c);
+    const bool delta = offsets && d_offsets && host_offsets_valid(offsets, width, nmajor, n);
+    const int pw = delta ? 1 : (bound <= 65536 ? 2 : 4);
+    const bool idx_pageable = host_is_pageable(indices), val_pageable = values && host_is_pageable(values);
+    const bool idx_pack_pointless = !delta && pw == width;  // u32 source, wide minor dimension: packed == raw
+    const bool vals_packable = values && vsz == 4;
+    constexpr int kChunkShift = 22;
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << kChunkShift);
+    const uint64_t nchunks = (n + chunk - 1) / chunk;
+    // ring slot: [index part: packed codes, or the raw integers of a pageable source][value part: packed, or staged raw]
+    const size_t idx_bytes = (chunk * (size_t)(idx_pageable ? width : pw) + 255) & ~size_t(255);
+    const size_t val_bytes = values ? (chunk * (val_pageable ? vsz : 2) + 255) & ~size_t(255) : 0;
+    const size_t slot_bytes = idx_bytes + val_bytes;
+    ensure_upload_ring(c, slot_bytes * srb_ctx::kUpSlots);
+    for (int i = 0; i < srb_ctx::kUpChunkEvents; ++i)
+        if (!c->up_cev[i]) SRB_CUDA(cudaEventCreateWithFlags(&c->up_cev[i], cudaEventDisableTiming));
+    Buf dpk = pw < 4 ? dev_alloc(s, n * pw) : Buf();            // packed index codes (pw = 4 lands in d_idx directly)
+    Buf draw = dev_alloc(s, chunk * (size_t)width);              // raw index chunk, narrowed right after its copy
+    Buf dvpk = vals_packable ? dev_alloc(s, nchunks * chunk * 2) : Buf();
+    std::vector<uint8_t> widths(nchunks, 0), raw_idx(nchunks, 0);
+    DeltaEscapes esc;
+    int vstate = vals_packable ? 1 : 0;  // 1: try u8, 2: try u16, 0: raw (sticky: a chunk that refuses widens all later ones)
+    bool oob = false, any_val_packed = false, any_idx_raw = false;
+    uint64_t link = 0, done = 0, enq_bytes = 0, done_bytes = 0;
+    std::vector<uint64_t> cum_bytes(nchunks + 1, 0);  // bytes enqueued up to and including chunk i - 1
+    double t_idx = 0.0, t_val = 0.0;                  // running estimates of the packing time of one chunk (ms)
+    int slot_use = 0;
+    const double rate = link_rate_bytes_per_ms();
+    uint64_t ci = 0;
+    for (uint64_t o = 0; o < n; o += chunk, ++ci) {
+        const uint64_t len = std::min<uint64_t>(chunk, n - o);
+        // how much copying is still queued on the link
+        while (done < ci && cudaEventQuery(c->up_cev[done % srb_ctx::kUpChunkEvents]) == cudaSuccess) ++done;
+        (void)cudaGetLastError();  // cudaErrorNotReady is not an error here
+        done_bytes = cum_bytes[done];
+        const double queued_ms = (double)(enq_bytes - done_bytes) / rate;
+        // every 32nd chunk is packed regardless, so a pessimistic first timing (cold pages, pool start-up) cannot lock
+        // the upload into the raw mode
+        const bool probe = ci % 32 == 0;
+        const bool pack_idx = !idx_pack_pointless && (idx_pageable || probe || queued_ms >= t_idx);
+        const bool try_val = vstate != 0 && (probe || queued_ms >= (pack_idx ? t_idx : 0.0) + t_val);
+        const bool need_slot = pack_idx || try_val || (values && val_pageable) || idx_pageable;
+        char *h_idx = nullptr, *h_val = nullptr;
+        if (need_slot) {
+            const int slot = slot_use++ % srb_ctx::kUpSlots;
+            if (c->up_ev_used[slot]) SRB_CUDA(cudaEventSynchronize(c->up_ev[slot]));  // the slot's previous copies are done
+            h_idx = (char *)c->up_ring + slot_bytes * slot, h_val = h_idx + idx_bytes;
+        }
+        uint64_t bytes = 0;
+        // ---- indices ----
+        if (pack_idx) {
+            const double t0 = host_now_ms();
+            if (delta) oob |= host_delta_encode(indices, offsets, width, nmajor, o, len, (uint8_t *)h_idx, bound, nthreads, esc);
+            else oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
+            const double dt = host_now_ms() - t0;
+            t_idx = t_idx == 0.0 ? dt : 0.5 * t_idx + 0.5 * dt;
+            char *dst = pw < 4 ? dpk->as<char>() + o * pw : (char *)(d_idx + o);
+            SRB_CUDA(cudaMemcpyAsync(dst, h_idx, len * pw, cudaMemcpyHostToDevice, s));
+            if (pw == 2) SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, len), 256, 0, s, dpk->as<uint16_t>() + o, d_idx + o, len, bound, d_flags);
+            bytes += len * pw;
+            ++c->last_upload_idx_packed;
+        } else {
+            // pinned (or pack-pointless) source: the DMA engine reads the caller's array directly
+            const char *src = (const char *)indices + o * width;
+            if (idx_pageable && h_idx) {
+                host_copy_parallel(src, h_idx, len * width, nthreads);
+                src = h_idx;
+            }
+            SRB_CUDA(cudaMemcpyAsync(draw->p, src, len * width, cudaMemcpyHostToDevice, s));
+            if (width == 8) SRB_LAUNCH((narrow_index_kernel<uint64_t>), grid_for(c, len), 256, 0, s, draw->as<uint64_t>(), d_idx + o, len, bound, d_flags);
+            else SRB_LAUNCH((narrow_index_kernel<uint32_t>), grid_for(c, len), 256, 0, s, draw->as<uint32_t>(), d_idx + o, len, bound, d_flags);
+            bytes += len * width;
+            raw_idx[ci] = 1, any_idx_raw = true;
+        }
+        // ---- values ----
+        if (values) {
+            const char *src = (const char *)values + o * vsz;
+            int w = 0;
+            if (try_val) {
+                const double t0 = host_now_ms();
+                while (vstate) {
+                    if (host_pack_values_f32((const float *)src, len, h_val, vstate, nthreads)) {
+                        w = vstate;
+                        break;
+                    }
+                    vstate = vstate == 1 ? 2 : 0;
+                }
+                const double dt = host_now_ms() - t0;
+                t_val = t_val == 0.0 ? dt : 0.5 * t_val + 0.5 * dt;
+            }
+            widths[ci] = (uint8_t)w;
+            if (w) {
+                SRB_CUDA(cudaMemcpyAsync(dvpk->as<char>() + 2 * o, h_val, len * w, cudaMemcpyHostToDevice, s));
+                bytes += len * w;
+                any_val_packed = true;
+                ++c->last_upload_val_packed;
+            } else {
+                if (val_pageable) {
+                    host_copy_parallel(src, h_val, len * vsz, nthreads);
+                    src = h_val;
+                }
+                SRB_CUDA(cudaMemcpyAsync((char *)d_val + o * vsz, src, len * vsz, cudaMemcpyHostToDevice, s));
+                bytes += len * vsz;
+            }
+        }
+        if (need_slot) {
+            const int slot = (slot_use - 1) % srb_ctx::kUpSlots;
+            SRB_CUDA(cudaEventRecord(c->up_ev[slot], s));
+            c->up_ev_used[slot] = true;
+        }
+        if (ci >= (uint64_t)srb_ctx::kUpChunkEvents && done + srb_ctx::kUpChunkEvents <= ci) {
+            // the event about to be reused belongs to a chunk that has not been seen complete yet
+            SRB_CUDA(cudaEventSynchronize(c->up_cev[ci % srb_ctx::kUpChunkEvents]));
+            done = ci - srb_ctx::kUpChunkEvents + 1;
+        }
+        SRB_CUDA(cudaEventRecord(c->up_cev[ci % srb_ctx::kUpChunkEvents], s));
+        enq_bytes += bytes, link += bytes;
+        cum_bytes[ci + 1] = enq_bytes;
+    }
+    c->last_upload_chunks = (int)nchunks;
+    bool sync_needed = false;
+    if (delta && c->last_upload_idx_packed) {
+        const uint64_t ne = esc.pos.size();
+        Buf dpos = dev_alloc(s, 8 * std::max<uint64_t>(ne, 1)), dval = dev_alloc(s, 4 * std::max<uint64_t>(ne, 1));
+        if (ne) {
+            SRB_CUDA(cudaMemcpyAsync(dpos->p, esc.pos.data(), 8 * ne, cudaMemcpyHostToDevice, s));
+            SRB_CUDA(cudaMemcpyAsync(dval->p, esc.val.data(), 4 * ne, cudaMemcpyHostToDevice, s));
+            link += 12 * ne;
+        }
+        Buf draw_flags;
+        if (any_idx_raw) {
+            draw_flags = dev_alloc(s, nchunks);
+            SRB_CUDA(cudaMemcpyAsync(draw_flags->p, raw_idx.data(), nchunks, cudaMemcpyHostToDevice, s));
+        }
+        const unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nmajor + 7) / 8, (uint64_t)c->sm_count * 16));
+        SRB_LAUNCH(delta_decode_kernel, g, 256, 0, s, dpk->as<uint8_t>(), d_offsets, nmajor, dpos->as<uint64_t>(), dval->as<uint32_t>(), ne, bound, d_idx,
+                   d_flags, any_idx_raw ? draw_flags->as<uint8_t>() : (const uint8_t *)nullptr, kChunkShift);
+        sync_needed = true;  // `esc`, `raw_idx` (pageable) and the escape buffers are done with
+    }
+    if (any_val_packed) {
+        Buf dw = dev_alloc(s, nchunks);
+        SRB_CUDA(cudaMemcpyAsync(dw->p, widths.data(), nchunks, cudaMemcpyHostToDevice, s));
+        SRB_LAUNCH(unpack_values_kernel, grid_for(c, n), 256, 0, s, dvpk->as<uint8_t>(), (float *)d_val, n, kChunkShift, dw->as<uint8_t>());
+        sync_needed = true;  // `widths` (pageable) and the staging ring are done with
+    }
+    if (sync_needed || oob) SRB_CUDA(cudaStreamSynchronize(s));
+    if (oob) throw Error(SRB_ERR_INDEX_OOB, "minor index out of bounds");
+    return link;
+}
 }  // namespace srb
 
 using namespace srb;
@@ -311,7 +493,8 @@ int32_t srb_ctx_set_upload_mode(srb_ctx *ctx, int32_t mode) {
     SRB_API_BEGIN
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
     SRB_REQUIRE(mode == SRB_UPLOAD_DEVICE_NARROW || mode == SRB_UPLOAD_HOST_PACK || mode == SRB_UPLOAD_AUTO ||
-                    mode == SRB_UPLOAD_HOST_PACK_VALUES || mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE || mode == SRB_UPLOAD_HOST_PACK_DELTA,
+                    mode == SRB_UPLOAD_HOST_PACK_VALUES || mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE || mode == SRB_UPLOAD_HOST_PACK_DELTA ||
+                    mode == SRB_UPLOAD_BALANCED,
                 SRB_ERR_INVALID_ARG, "bad upload mode");
     ctx->upload_mode = mode;
     SRB_API_END
@@ -322,6 +505,15 @@ int32_t srb_ctx_last_upload(srb_ctx *ctx, uint64_t *h2d_bytes, int32_t *host_pac
     SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
     if (h2d_bytes) *h2d_bytes = ctx->last_upload_h2d;
     if (host_packed) *host_packed = ctx->last_upload_packed;
+    SRB_API_END
+}
+
+int32_t srb_ctx_last_upload_chunks(srb_ctx *ctx, int32_t *chunks, int32_t *index_chunks_packed, int32_t *value_chunks_packed) {
+    SRB_API_BEGIN
+    SRB_REQUIRE(ctx, SRB_ERR_INVALID_ARG, "null ctx");
+    if (chunks) *chunks = ctx->last_upload_chunks;
+    if (index_chunks_packed) *index_chunks_packed = ctx->last_upload_idx_packed;
+    if (value_chunks_packed) *value_chunks_packed = ctx->last_upload_val_packed;
     SRB_API_END
 }
 
@@ -351,8 +543,9 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
         upload_convert<int64_t>(ctx, offsets, SRB_U32, nmajor + 1, st->offsets->as<int64_t>());
     }
     const int up_mode = effective_upload_mode(ctx, nnz);
+    const bool balanced = up_mode == SRB_UPLOAD_BALANCED;
     const bool packed = up_mode == SRB_UPLOAD_HOST_PACK || up_mode == SRB_UPLOAD_HOST_PACK_VALUES || up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ||
-                        up_mode == SRB_UPLOAD_HOST_PACK_DELTA;
+                        up_mode == SRB_UPLOAD_HOST_PACK_DELTA || balanced;
     if (!packed) upload_indices(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>());
     std::unique_ptr<srb_mat> m(new srb_mat());
     m->ctx = ctx, m->format = format, m->nrows = nrows, m->ncols = ncols, m->st = st;
@@ -364,7 +557,10 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
     // values whose host dtype is the device storage dtype travel as they are, interleaved with the index chunks
     const bool direct = (dtype == SRB_F32 && f32_exact) || (dtype == SRB_F64 && !f32_exact);
     uint64_t link_bytes = 0;
-    if (packed)
+    if (balanced)
+        link_bytes = upload_balanced(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
+                                     direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p, offsets, nmajor, st->offsets->as<int64_t>());
+    else if (packed)
         link_bytes = upload_packed(ctx, indices, idx_width, nnz, nminor, st->indices->as<uint32_t>(), flags->as<uint32_t>(),
                                    direct ? values : nullptr, f32_exact ? 4 : 8, m->values->p,
                                    up_mode == SRB_UPLOAD_HOST_PACK_VALUES ? 1 : up_mode == SRB_UPLOAD_HOST_PACK_ADAPTIVE ? 2 : 0,
@@ -377,7 +573,8 @@ int32_t srb_mat_upload(srb_ctx *ctx, int32_t format, uint64_t nrows, uint64_t nc
         static const size_t esz[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
         ctx->last_upload_h2d = (uint64_t)idx_width * (nmajor + 1) +
                                (packed ? link_bytes + (direct ? 0 : esz[dtype] * nnz) : ((uint64_t)idx_width + esz[dtype]) * nnz);
-        ctx->last_upload_packed = packed ? 1 : 0;
+        ctx->last_upload_packed = balanced ? (ctx->last_upload_idx_packed > 0 ? 1 : 0) : (packed ? 1 : 0);
+        if (!balanced) ctx->last_upload_chunks = ctx->last_upload_idx_packed = ctx->last_upload_val_packed = 0;
     }
     if (nmajor) SRB_LAUNCH(canonical_check_kernel, grid_for(ctx, nmajor * 32), 256, 0, s, st->offsets->as<int64_t>(), st->indices->as<uint32_t>(), nmajor, nnz, flags->as<uint32_t>());
     uint32_t hflags[2];

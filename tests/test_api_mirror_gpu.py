@@ -124,7 +124,7 @@ def test_two_gpu_row_sharding_matches_single_gpu():
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29655", os.path.join(ROOT, "tests", "multigpu_check.py")],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTIGPU OK" in r.stdout
 

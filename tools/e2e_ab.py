@@ -38,10 +38,11 @@ emit({"what": "setup", "nnz": nnz, "pin_and_download_s": time.time() - t0, "thre
       "cpus": os.cpu_count()})
 stream = torch.cuda.ExternalStream(ctx.stream)
 ref_sum = None
-for mode, name in ((_ffi.UPLOAD_DEVICE_NARROW, "device_narrow"), (_ffi.UPLOAD_HOST_PACK, "host_pack"),
-                   (_ffi.UPLOAD_HOST_PACK_VALUES, "host_pack_values"), (_ffi.UPLOAD_HOST_PACK_ADAPTIVE, "host_pack_adaptive"), (_ffi.UPLOAD_HOST_PACK_DELTA, "host_pack_delta"),
-                   (_ffi.UPLOAD_DEVICE_NARROW, "device_narrow"),
-                   (_ffi.UPLOAD_HOST_PACK, "host_pack")):
+ALL = ((_ffi.UPLOAD_DEVICE_NARROW, "device_narrow"), (_ffi.UPLOAD_HOST_PACK, "host_pack"),
+       (_ffi.UPLOAD_HOST_PACK_VALUES, "host_pack_values"), (_ffi.UPLOAD_HOST_PACK_ADAPTIVE, "host_pack_adaptive"),
+       (_ffi.UPLOAD_HOST_PACK_DELTA, "host_pack_delta"), (_ffi.UPLOAD_BALANCED, "balanced"))
+want = os.environ.get("AB_MODES")
+for mode, name in [x for x in ALL if (not want or x[1] in want.split(","))]:
     ctx.set_upload_mode(mode)
     for what in ("upload", "e2e"):
         ts = []
@@ -65,5 +66,6 @@ for mode, name in ((_ffi.UPLOAD_DEVICE_NARROW, "device_narrow"), (_ffi.UPLOAD_HO
                 assert np.array_equal(s, ref_sum), "upload modes disagree"
             mt.free()
         emit({"what": what, "mode": name, "event_ms": [round(t[0], 2) for t in ts], "wall_ms": [round(t[1], 2) for t in ts],
-              "cells_per_s": n / (min(t[0] for t in ts) * 1e-3)})
+              "cells_per_s": n / (min(t[0] for t in ts) * 1e-3), "h2d_bytes": ctx.last_upload()[0],
+              "chunks_idx_val_packed": ctx.last_upload_chunks()})
 ctx.close()
