@@ -109,11 +109,14 @@ __global__ void __launch_bounds__(256) symv_cols_kernel(const double *__restrict
     const uint32_t warp = (blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = gridDim.x * 8;
     for (uint32_t col = warp; col < d; col += nwarps) {
         const double *c = C + (size_t)col * d;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t i = lane;
-        for (; i + 96 < d; i += 128) a0 += c[i] * v[i], a1 += c[i + 32] * v[i + 32], a2 += c[i + 64] * v[i + 64], a3 += c[i + 96] * v[i + 96];
-        for (; i < d; i += 32) a0 += c[i] * v[i];
-        const double acc = warp_sum((a0 + a1) + (a2 + a3));
+        for (; i + 224 < d; i += 256) {  // 8 independent 256-byte warp loads in flight
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += c[i + 32 * u] * v[i + 32 * u];
+        }
+        for (; i < d; i += 32) a[0] += c[i] * v[i];
+        const double acc = warp_sum(((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7])));
         if (lane == 0) w[col] = acc, cv[col] = acc;
     }
 }
@@ -143,14 +146,16 @@ __global__ void __launch_bounds__(1024) lanczos_init_kernel(double *__restrict__
 }
 // One CTA: w = V[:, j+1] (holding C v_j) is orthogonalised twice against V[:, 0..j] (CGS2), beta_j = ||w|| goes to
 // sc[2 + j], v_{j+1} = w / beta_j. sc[1] = ||C v_0|| is the reference magnitude of the breakdown test (flag[0]).
-// Dynamic shared memory: w (d doubles) + the coefficients h (j + 1 doubles).
+// The coefficients h = V^T w are formed 8 basis columns at a time with every thread summing over its own elements
+// (8 x elements-per-thread independent loads in flight; a first version with one warp per column was latency-bound:
+// 45 us per step). Dynamic shared memory: w (d doubles) + h (j + 1) + the per-warp partial sums (32 x 8).
 __global__ void __launch_bounds__(1024) lanczos_orth_kernel(double *__restrict__ V, uint32_t d, int j, double *__restrict__ sc,
                                                             uint32_t *__restrict__ flag) {
     extern __shared__ double lz[];
     __shared__ double sh[32];
-    double *w = lz, *h = lz + d;
+    double *w = lz, *h = lz + d, *part = h + (j + 1);  // part[8][32]
     double *wg = V + (size_t)(j + 1) * d;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double nrm0 = 0.0;
     for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
         const double x = wg[i];
@@ -161,14 +166,26 @@ __global__ void __launch_bounds__(1024) lanczos_orth_kernel(double *__restrict__
     if (j == 0 && threadIdx.x == 0) sc[1] = sqrt(nrm0);
     __syncthreads();
     for (int pass = 0; pass < 2; ++pass) {
-        for (int c = (int)warp; c <= j; c += (int)nw) {  // h = V^T w: one warp per basis column
-            const double *vc = V + (size_t)c * d;
-            double a = 0.0;
-            for (uint32_t i = lane; i < d; i += 32) a += vc[i] * w[i];
-            a = warp_sum(a);
-            if (lane == 0) h[c] = a;
+        for (int c0 = 0; c0 <= j; c0 += 8) {
+            double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {
+                const double wi = w[i];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (c0 + u <= j) a[u] += V[(size_t)(c0 + u) * d + i] * wi;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double r = warp_sum(a[u]);
+                if (lane == 0) part[u * 32 + warp] = r;
+            }
+            __syncthreads();
+            if (warp < 8 && c0 + (int)warp <= j) {
+                const double r = warp_sum(part[warp * 32 + lane]);
+                if (lane == 0) h[c0 + warp] = r;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         for (uint32_t i = threadIdx.x; i < d; i += blockDim.x) {  // w -= V h
             double x = w[i];
             for (int c = 0; c <= j; ++c) x -= V[(size_t)c * d + i] * h[c];
@@ -200,6 +217,53 @@ __global__ void __launch_bounds__(128) krylov_project_kernel(const double *__res
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) H[(size_t)a * L + b] = (sh[0] + sh[1]) + (sh[2] + sh[3]);
+}
+
+// Cholesky factor of the b x b Gram matrix of the block (CholeskyQR), one CTA, the triangle held in shared memory
+// (b (b + 1) / 2 doubles: 148 KB at b = 192). G is column-major with the UPPER triangle valid; on exit the upper triangle
+// holds R with G = R^T R (what cusolverDnDpotrf(UPPER) leaves, at a quarter of its ~0.2 ms). info = the 1-based index of a
+// non-positive / non-finite pivot, else 0. Right-looking: column k is scaled, then the trailing triangle is updated.
+__global__ void __launch_bounds__(1024) chol_upper_kernel(double *__restrict__ G, uint32_t b, int *__restrict__ info) {
+    extern __shared__ double Lt[];  // L[i][j], j <= i, at i (i + 1) / 2 + j   (L = R^T)
+    __shared__ double s_piv;
+    __shared__ int s_bad;
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t e = tid; e < b * b; e += nt) {
+        const uint32_t i = e % b, j = e / b;  // G(i, j), column-major
+        if (i <= j) Lt[(size_t)j * (j + 1) / 2 + i] = G[e];
+    }
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (uint32_t k = 0; k < b; ++k) {
+        if (tid == 0) {
+            const double p = Lt[(size_t)k * (k + 1) / 2 + k];
+            if (!(p > 0.0) || !isfinite(p)) {
+                if (!s_bad) s_bad = (int)k + 1;
+                s_piv = 1.0;
+            } else {
+                s_piv = sqrt(p);
+            }
+        }
+        __syncthreads();
+        const double piv = s_piv;
+        for (uint32_t i = k + tid; i < b; i += nt) {
+            double &x = Lt[(size_t)i * (i + 1) / 2 + k];
+            x = i == k ? piv : x / piv;
+        }
+        __syncthreads();
+        // trailing update: L[i][j] -= L[i][k] L[j][k] for k < j <= i < b; one warp per row, lanes along the row
+        for (uint32_t i = k + 1 + (tid >> 5); i < b; i += nt >> 5) {
+            double *row = Lt + (size_t)i * (i + 1) / 2;
+            const double lik = row[k];
+            for (uint32_t j = k + 1 + (tid & 31); j <= i; j += 32) row[j] -= lik * Lt[(size_t)j * (j + 1) / 2 + k];
+        }
+        __syncthreads();
+    }
+    for (uint32_t e = tid; e < b * b; e += nt) {
+        const uint32_t i = e % b, j = e / b;
+        if (i <= j) G[e] = Lt[(size_t)j * (j + 1) / 2 + i];
+    }
+    if (tid == 0) *info = s_bad;
 }
 
 // cyclic Jacobi on a small symmetric matrix (row-major n x n, destroyed); eigenvalues ascending, vecs[i * n + j] =
@@ -284,11 +348,11 @@ struct PhaseTrace {
 static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, cudaStream_t es, double *d_C, uint32_t d, uint32_t k,
                        double *d_evals) {
     // tunables (round-2 sweeps without a rebuild; the defaults are the measured configuration):
-    //   SRB_CHFSI_KRYLOV  Krylov steps for the bounds (8..40, default 40)   SRB_CHFSI_BLOCK  block width b (multiple of 32)
+    //   SRB_CHFSI_KRYLOV  Krylov steps for the bounds (8..40, default 24)   SRB_CHFSI_BLOCK  block width b (multiple of 32)
     //   SRB_CHFSI_TARGET  log10 of the gain of the k-th eigenvalue over the cut per outer round (default 11)
     static const int L = [] {
         const char *e = getenv("SRB_CHFSI_KRYLOV");
-        return e ? std::max(8, std::min(40, atoi(e))) : 40;
+        return e ? std::max(8, std::min(40, atoi(e))) : 24;
     }();
     static const uint32_t b_env = [] {
         const char *e = getenv("SRB_CHFSI_BLOCK");
@@ -300,7 +364,9 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
     }();
     constexpr int kMaxOuter = 6, kMaxRounds = 24, kMaxDegree = 32, kMaxProducts = 400;
     constexpr double kAmpCap = 1e8, kTol = 1e-11;
-    uint32_t b = std::min<uint32_t>(d / 4, ((std::max<uint32_t>(3 * k, k + 96) + 63) / 64) * 64);
+    // block width: 3 k (or k + 96) rounded up to 32 — 160 at k = 50 (measured at the bench size: 6.7 ms against 7.5 ms for 192:
+    // the same 51 block products, each narrower, and a smaller Rayleigh-Ritz problem)
+    uint32_t b = std::min<uint32_t>(d / 4, ((std::max<uint32_t>(3 * k, k + 96) + 31) / 32) * 32);
     if (b_env >= k + 16 && b_env <= d / 2) b = b_env;
     if (b < k + 16 || d < 512) return false;
     const double one = 1.0, zero = 0.0, minus1 = -1.0;
@@ -320,14 +386,32 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
     int lw_potrf = 0, lw_syevd = 0;
     SRB_CUSOLVER(cusolverDnDpotrf_bufferSize(so, CUBLAS_FILL_MODE_UPPER, (int)b, G, (int)b, &lw_potrf));
     SRB_CUSOLVER(cusolverDnDsyevd_bufferSize(so, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)b, G, (int)b, theta, &lw_syevd));
-    Buf bwork = dev_alloc(es, 8 * (size_t)std::max(std::max(lw_potrf, lw_syevd), 1));
+    // SRB_CHFSI_RR=syevj: Jacobi instead of divide-and-conquer for the b x b Rayleigh-Ritz problem (probe)
+    static const bool rr_jacobi = [] {
+        const char *e = getenv("SRB_CHFSI_RR");
+        return e && !strcmp(e, "syevj");
+    }();
+    syevjInfo_t jinfo = nullptr;
+    int lw_syevj = 0;
+    if (rr_jacobi) {
+        SRB_CUSOLVER(cusolverDnCreateSyevjInfo(&jinfo));
+        cusolverDnXsyevjSetTolerance(jinfo, 1e-15);
+        cusolverDnXsyevjSetMaxSweeps(jinfo, 30);
+        cusolverDnXsyevjSetSortEig(jinfo, 1);
+        SRB_CUSOLVER(cusolverDnDsyevj_bufferSize(so, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)b, G, (int)b, theta, &lw_syevj, jinfo));
+    }
+    struct JGuard {
+        syevjInfo_t p;
+        ~JGuard() { if (p) cusolverDnDestroySyevjInfo(p); }
+    } jguard{jinfo};
+    Buf bwork = dev_alloc(es, 8 * (size_t)std::max(std::max(std::max(lw_potrf, lw_syevd), lw_syevj), 1));
     double *work = bwork->as<double>();
     SRB_CUBLAS(cublasSetStream(bl, es));
     PhaseTrace trace(es);
 
     // ---- 1. Krylov bounds: v_{j+1} = normalise((I - V V^T)^2 C v_j), two own launches per step ----
-    if ((size_t)8 * (d + L + 1) > ctx->smem_optin) return false;  // w must fit one CTA's shared memory: syevd instead
-    const size_t lz_smem = 8 * ((size_t)d + L + 1);
+    if ((size_t)8 * (d + L + 1 + 256) > ctx->smem_optin) return false;  // w must fit one CTA's shared memory: syevd instead
+    const size_t lz_smem = 8 * ((size_t)d + L + 1 + 256);
     SRB_CUDA(cudaFuncSetAttribute(lanczos_orth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lz_smem));
     SRB_LAUNCH(lanczos_init_kernel, 1, 1024, 0, es, V, d, 0x5EEDC0DEull);
     for (int j = 0; j < L; ++j) {
@@ -368,9 +452,19 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
 
     // ---- 2./3. filter + Rayleigh-Ritz ----
     SRB_LAUNCH(fill_random_kernel, (unsigned)std::min<size_t>((db + 255) / 256, 4096), 256, 0, es, Y, (uint64_t)db, 0xC4EB5EEDull);
+    const size_t chol_smem = 8 * (size_t)b * (b + 1) / 2;
+    // SRB_CHFSI_CHOL=own selects the single-CTA kernel (measured SLOWER than cusolverDnDpotrf in its unblocked form: 0.38 vs
+    // 0.2 ms at b = 192 — one latency-bound column at a time; kept for a blocked rewrite)
+    static const bool want_own_chol = [] {
+        const char *e = getenv("SRB_CHFSI_CHOL");
+        return e && !strcmp(e, "own");
+    }();
+    const bool own_chol = want_own_chol && chol_smem + 1024 <= ctx->smem_optin;
+    if (own_chol) SRB_CUDA(cudaFuncSetAttribute(chol_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     auto cholqr = [&](double *Ycur) {
         SRB_CUBLAS(cublasDsyrk(bl, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_T, (int)b, (int)d, &one, Ycur, (int)d, &zero, G, (int)b));
-        SRB_CUSOLVER(cusolverDnDpotrf(so, CUBLAS_FILL_MODE_UPPER, (int)b, G, (int)b, work, lw_potrf, infos + n_info));
+        if (own_chol) SRB_LAUNCH(chol_upper_kernel, 1, 1024, chol_smem, es, G, b, infos + n_info);
+        else SRB_CUSOLVER(cusolverDnDpotrf(so, CUBLAS_FILL_MODE_UPPER, (int)b, G, (int)b, work, lw_potrf, infos + n_info));
         ++n_info;
         SRB_CUBLAS(cublasDtrsm(bl, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_UPPER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, (int)d, (int)b, &one, G, (int)b, Ycur, (int)d));
     };
@@ -386,9 +480,14 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         const double amp = std::cosh(m * std::acosh(xk));
         int rounds = (int)std::ceil(std::log(kTarget) / std::log(std::max(amp, 1.0001)));
         rounds = std::max(1, std::min(rounds, outer == 0 ? 3 : kMaxRounds));
+        // the smallest degree that reaches the target in exactly `rounds` rounds (a ceil() on the round count would
+        // otherwise overshoot by up to a whole round: 76 instead of 51 block products at the bench size)
+        const int m_full = m;
+        const int m_trim = (int)std::ceil(std::acosh(std::pow(kTarget, 1.0 / rounds)) / std::acosh(xk));
+        const int m_use = std::max(2, std::min(m_full, m_trim));
         if (n_info + 2 * rounds + 1 > 60) return false;
         // work budget: beyond ~400 block products the iteration would cost more than the syevd it replaces
-        if (st.block_products + rounds * m > kMaxProducts) return false;
+        if (st.block_products + rounds * m_use > kMaxProducts) return false;
         trace.mark(4);
         SRB_LAUNCH(shift_copy_kernel, (unsigned)((dd + 255) / 256), 256, 0, es, d_C, Cs, d, c);
         for (int r = 0; r < rounds; ++r) {
@@ -397,13 +496,13 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
             double sigma = sigma1, a1 = sigma1 / e;
             SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)d, &a1, Cs, (int)d, Y, (int)d, &zero, Yb, (int)d));
             double *Yp = Y, *Yc = Yb;
-            for (int i = 2; i <= m; ++i) {
+            for (int i = 2; i <= m_use; ++i) {
                 const double sn = 1.0 / (2.0 / sigma1 - sigma), al = 2.0 * sn / e, be = -sigma * sn;
                 SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)d, &al, Cs, (int)d, Yc, (int)d, &be, Yp, (int)d));
                 std::swap(Yp, Yc);
                 sigma = sn;
             }
-            st.block_products += m;
+            st.block_products += m_use;
             if (Yc != Y) std::swap(Y, Yb);  // Y = filtered block, Yb = scratch
             trace.mark(1);
             cholqr(Y);
@@ -415,7 +514,10 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)d, &one, d_C, (int)d, Y, (int)d, &zero, W, (int)d));
         SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_T, CUBLAS_OP_N, (int)b, (int)b, (int)d, &one, Y, (int)d, W, (int)d, &zero, G, (int)b));
         SRB_LAUNCH(symmetrize_kernel, (b * b + 255) / 256, 256, 0, es, G, b);
-        SRB_CUSOLVER(cusolverDnDsyevd(so, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)b, G, (int)b, theta, work, lw_syevd, infos + n_info));
+        if (rr_jacobi)
+            SRB_CUSOLVER(cusolverDnDsyevj(so, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)b, G, (int)b, theta, work, lw_syevj, infos + n_info, jinfo));
+        else
+            SRB_CUSOLVER(cusolverDnDsyevd(so, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, (int)b, G, (int)b, theta, work, lw_syevd, infos + n_info));
         ++n_info;
         ++st.block_products, ++st.rayleigh_ritz;
         SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)b, &one, Y, (int)d, G, (int)b, &zero, Yb, (int)d));

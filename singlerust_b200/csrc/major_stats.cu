@@ -5,6 +5,10 @@
 // HBM-bound: 4 B/nnz (f32 values) + 8 B/line of offsets; column indices are never read.
 // Mapping: LPR lanes cooperate on one line (LPR = 32 for long lines, 8 for short ones), coalesced strided
 // loads with 4 independent loads in flight per lane, f64 accumulation, shuffle tree at the end.
+#include <algorithm>
+#include <cstdlib>
+
+#include "bulk.cuh"
 #include "common.cuh"
 
 namespace srb {
@@ -144,6 +148,120 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K1, bulk-staged form (f32 values, sum / range / flags): the contiguous run of values that belongs to a CTA's rows is
+// streamed tile by tile (2048 values = 8 KB) into a 4-stage shared-memory ring by cp.async.bulk (one producer thread; the
+// copy engine keeps up to 32 KB per CTA, ~220 KB per SM, in flight without a register or an issue slot of the reducing
+// warps), and two consumer warps reduce whole rows out of shared memory: lane-strided conflict-free reads, f64 partial
+// sums per lane, warp-shuffle / redux at the end of the row. A tile holds ~1.4 rows of the bench matrix, so the two
+// consumer warps of a CTA work on neighbouring rows of the same tile; parallelism comes from 7 resident CTAs per SM.
+// Every consumer warp waits for and releases every tile exactly once, in order (rows may span tiles).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace k1b {
+constexpr int TILE = 2048, STAGES = 4, CONSUMERS = 2, THREADS = 32 * (1 + CONSUMERS);
+}
+
+__global__ void __launch_bounds__(k1b::THREADS) major_sum_bulk_kernel(const int64_t *__restrict__ off, const float *__restrict__ val,
+                                                                      uint64_t nmajor, uint32_t rows_per_cta, double *__restrict__ o_sum,
+                                                                      double *__restrict__ o_max, double *__restrict__ o_min,
+                                                                      uint32_t *__restrict__ flags) {
+    using namespace k1b;
+    __shared__ __align__(128) float tile[STAGES][TILE];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
+    if (r0 >= nmajor) return;
+    const uint64_t r1 = min(r0 + (uint64_t)rows_per_cta, nmajor);
+    const int64_t a0 = off[r0], b1 = off[r1];
+    const int64_t base = a0 & ~(int64_t)3;  // 16-byte aligned start of the CTA's run
+    const uint32_t ntiles = (uint32_t)((b1 - base + TILE - 1) / TILE);
+    const uint32_t full0 = bulk::smem_u32(&bars[0]), empty0 = bulk::smem_u32(&bars[STAGES]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) bulk::mbar_init(full0 + 8 * s, 1), bulk::mbar_init(empty0 + 8 * s, CONSUMERS);
+        bulk::mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            for (uint32_t t = 0; t < ntiles; ++t) {
+                const uint32_t s = t % STAGES;
+                bulk::mbar_wait(empty0 + 8 * s, ((t / STAGES) & 1) ^ 1);
+                const int64_t lo = base + (int64_t)t * TILE;
+                const uint32_t n = (uint32_t)min((int64_t)TILE, (b1 - lo + 3) & ~(int64_t)3);  // whole 16-byte units
+                bulk::mbar_arrive_expect_tx(full0 + 8 * s, 4 * n);
+                bulk::copy_g2s(bulk::smem_u32(&tile[s][0]), val + lo, 4 * n, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+    const uint32_t cw = warp - 1;
+    uint32_t t_cur = 0, bad = 0;
+    bool have = false;  // tile t_cur has been waited for
+    auto release_until = [&](uint32_t t) {  // wait for and release the tiles before t
+        while (t_cur < t) {
+            if (!have) bulk::mbar_wait(full0 + 8 * (t_cur % STAGES), (t_cur / STAGES) & 1);
+            __syncwarp();
+            if (lane == 0) bulk::mbar_arrive(empty0 + 8 * (t_cur % STAGES));
+            ++t_cur, have = false;
+        }
+    };
+    for (uint64_t r = r0 + cw; r < r1; r += CONSUMERS) {
+        const int64_t a = off[r], b = off[r + 1];
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        uint32_t orbits = 0, maxab = 0, minab1 = 0xFFFFFFFFu, nonint = 0;
+        int64_t pos = a;
+        while (pos < b) {
+            const uint32_t t = (uint32_t)((pos - base) / TILE);
+            release_until(t);
+            if (!have) bulk::mbar_wait(full0 + 8 * (t % STAGES), (t / STAGES) & 1), have = true;
+            const int64_t tile_lo = base + (int64_t)t * TILE;
+            const int e = (int)(min(b, tile_lo + TILE) - tile_lo);
+            const float *tp = tile[t % STAGES];
+            int i = (int)(pos - tile_lo) + (int)lane;
+#define SRB_K1_TRACK(V)                                                       \
+    do {                                                                      \
+        const uint32_t bits = __float_as_uint(V), ab = bits & 0x7FFFFFFFu;    \
+        orbits |= bits;                                                       \
+        maxab = max(maxab, ab);                                               \
+        minab1 = min(minab1, ab - 1u);                                        \
+        nonint |= (uint32_t)((V) != truncf(V));                               \
+    } while (0)
+            for (; i + 96 < e; i += 128) {
+                const float v0 = tp[i], v1 = tp[i + 32], v2 = tp[i + 64], v3 = tp[i + 96];
+                SRB_K1_TRACK(v0);
+                SRB_K1_TRACK(v1);
+                SRB_K1_TRACK(v2);
+                SRB_K1_TRACK(v3);
+                s0 += (double)v0, s1 += (double)v1, s2 += (double)v2, s3 += (double)v3;
+            }
+            for (; i < e; i += 32) {
+                const float v0 = tp[i];
+                SRB_K1_TRACK(v0);
+                s0 += (double)v0;
+            }
+#undef SRB_K1_TRACK
+            pos = tile_lo + e;
+        }
+        const double sum = warp_sum((s0 + s1) + (s2 + s3));
+        maxab = __reduce_max_sync(0xffffffffu, maxab);
+        minab1 = __reduce_min_sync(0xffffffffu, minab1);
+        orbits = __reduce_or_sync(0xffffffffu, orbits);
+        nonint = __reduce_or_sync(0xffffffffu, nonint);
+        if (lane == 0) {
+            o_sum[r] = sum;
+            o_max[r] = (double)__uint_as_float(maxab);
+            o_min[r] = (minab1 == 0xFFFFFFFFu) ? INFINITY : (double)__uint_as_float(minab1 + 1u);
+        }
+        bad |= (orbits >> 31) | (2u * (uint32_t)(maxab >= 0x7F800000u)) | (4u * nonint);
+    }
+    release_until(ntiles);
+    if (lane == 0 && bad) {
+        if (bad & 1u) atomicOr(flags, 1u);
+        if (bad & 2u) atomicOr(flags + 1, 1u);
+        if (bad & 4u) atomicOr(flags + 2, 1u);
+    }
+}
+
 template <int MODE>
 static void launch_major(srb_mat *m, double *o0, double *o1, double *o2, uint32_t *flags) {
     srb_ctx *c = m->ctx;
@@ -169,14 +287,28 @@ static void launch_major(srb_mat *m, double *o0, double *o1, double *o2, uint32_
 void major_sum_absmax(srb_mat *m) {
     if (m->has_pending()) materialize(m, false);
     if (m->major.valid) return;
-    cudaStream_t st = m->ctx->stream;
+    srb_ctx *c = m->ctx;
+    cudaStream_t st = c->stream;
     const uint64_t n = m->nmajor();
     m->major.sum = dev_zeros(st, sizeof(double) * (n + 1));
     m->major.absmax = dev_zeros(st, sizeof(double) * (n + 1));
     m->major.absmin = dev_zeros(st, sizeof(double) * (n + 1));
     m->major.flags = dev_zeros(st, sizeof(uint32_t) * 4);
-    launch_major<MODE_SUM_ABSMAX>(m, m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(),
-                                  m->major.flags->as<uint32_t>());
+    static const int bulk_on = [] {
+        const char *e = getenv("SRB_K1_BULK");
+        return (e && e[0] == '0') ? 0 : 1;
+    }();
+    // bulk-staged kernel: f32 storage and lines long enough that a tile holds only a few of them
+    if (bulk_on && n && m->vdtype == SRB_F32 && (double)m->st->nnz / (double)n >= 128.0) {
+        uint64_t rpc = (n + (uint64_t)c->sm_count * 28 - 1) / ((uint64_t)c->sm_count * 28);
+        rpc = std::max<uint64_t>(16, std::min<uint64_t>(rpc, 4096));
+        const unsigned grid = (unsigned)((n + rpc - 1) / rpc);
+        SRB_LAUNCH(major_sum_bulk_kernel, grid, k1b::THREADS, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
+                   m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
+    } else {
+        launch_major<MODE_SUM_ABSMAX>(m, m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(),
+                                      m->major.flags->as<uint32_t>());
+    }
     m->major.valid = true;
 }
 

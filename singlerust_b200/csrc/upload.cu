@@ -360,21 +360,41 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
     uint64_t link = 0, done = 0, enq_bytes = 0, done_bytes = 0;
     std::vector<uint64_t> cum_bytes(nchunks + 1, 0);  // bytes enqueued up to and including chunk i - 1
     double t_idx = 0.0, t_val = 0.0;                  // running estimates of the packing time of one chunk (ms)
+    double acc_raw = 0.0, acc_val = 0.0;              // dithering accumulators of the raw-index / packed-value fractions
     int slot_use = 0;
     const double rate = link_rate_bytes_per_ms();
     uint64_t ci = 0;
     for (uint64_t o = 0; o < n; o += chunk, ++ci) {
         const uint64_t len = std::min<uint64_t>(chunk, n - o);
-        // how much copying is still queued on the link
+        // retire completed chunks (keeps the per-chunk events reusable; the decision itself is model-based, see below)
         while (done < ci && cudaEventQuery(c->up_cev[done % srb_ctx::kUpChunkEvents]) == cudaSuccess) ++done;
         (void)cudaGetLastError();  // cudaErrorNotReady is not an error here
         done_bytes = cum_bytes[done];
-        const double queued_ms = (double)(enq_bytes - done_bytes) / rate;
+        // Rate model. Per chunk of `len` entries: packing the indices costs the host t_idx (measured, running mean, with
+        // the DMA engine competing for the same memory) and the link len*pw bytes; sending them raw costs the host nothing
+        // and the link len*width bytes. With the values raw, host and link finish together when a fraction
+        //     g = (t_idx - t_k) / (t_idx - t_k + t_r)        t_k, t_r = link time of a packed / raw chunk (indices + values)
+        // of the chunks goes raw (g = 0 when the host packs faster than the link drains). Only when the host is FASTER than
+        // the link is the spare host time spent on packing values, for the fraction f of chunks that equalises the two.
+        const double t_ki = (double)len * pw / rate, t_ri = (double)len * width / rate;
+        const double t_vr = values ? (double)len * vsz / rate : 0.0, t_vp = values ? (double)len * (vstate == 2 ? 2 : 1) / rate : 0.0;
+        double g = 0.0, f = 0.0;
+        if (t_idx > 0.0) {
+            const double t_k = t_ki + t_vr, t_r = t_ri + t_vr;
+            if (t_idx > t_k) g = (t_idx - t_k) / (t_idx - t_k + t_r);
+            else if (vstate && t_val > 0.0) f = std::min(1.0, (t_k - t_idx) / (t_val + t_vr - t_vp));
+        }
         // every 32nd chunk is packed regardless, so a pessimistic first timing (cold pages, pool start-up) cannot lock
         // the upload into the raw mode
         const bool probe = ci % 32 == 0;
-        const bool pack_idx = !idx_pack_pointless && (idx_pageable || probe || queued_ms >= t_idx);
-        const bool try_val = vstate != 0 && (probe || queued_ms >= (pack_idx ? t_idx : 0.0) + t_val);
+        acc_raw += g, acc_val += f;
+        bool pack_idx = !idx_pack_pointless;
+        if (pack_idx && !idx_pageable && !probe && acc_raw >= 1.0) pack_idx = false, acc_raw -= 1.0;
+        bool try_val = false;
+        if (vstate != 0 && (probe || acc_val >= 1.0)) {
+            try_val = true;
+            if (!probe) acc_val -= 1.0;
+        }
         const bool need_slot = pack_idx || try_val || (values && val_pageable) || idx_pageable;
         char *h_idx = nullptr, *h_val = nullptr;
         if (need_slot) {
@@ -388,7 +408,7 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
             const double t0 = host_now_ms();
             if (delta) oob |= host_delta_encode(indices, offsets, width, nmajor, o, len, (uint8_t *)h_idx, bound, nthreads, esc);
             else oob |= host_pack_indices((const char *)indices + o * width, width, len, h_idx, pw, bound, nthreads);
-            const double dt = host_now_ms() - t0;
+            const double dt = (host_now_ms() - t0) * (double)chunk / (double)len;
             t_idx = t_idx == 0.0 ? dt : 0.5 * t_idx + 0.5 * dt;
             char *dst = pw < 4 ? dpk->as<char>() + o * pw : (char *)(d_idx + o);
             SRB_CUDA(cudaMemcpyAsync(dst, h_idx, len * pw, cudaMemcpyHostToDevice, s));
@@ -421,7 +441,7 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
                     }
                     vstate = vstate == 1 ? 2 : 0;
                 }
-                const double dt = host_now_ms() - t0;
+                const double dt = (host_now_ms() - t0) * (double)chunk / (double)len;
                 t_val = t_val == 0.0 ? dt : 0.5 * t_val + 0.5 * dt;
             }
             widths[ci] = (uint8_t)w;

@@ -73,3 +73,22 @@ def finalize_limbs(acc: np.ndarray, F: int):
             N = c * Q - S * S
             v_out[j] = math.ldexp(float(max(N, 0)) / (float(c) * float(c)), -2 * F)
     return cnt, s_out, q_out, v_out
+
+
+def tri_index(i: int, j: int, d: int) -> int:
+    """Position of G[i][j] (i <= j) in the packed upper triangle the ranks allreduce (csrc/pca.cu: tri_pack_kernel)."""
+    assert 0 <= i <= j < d
+    return i * d - i * (i - 1) // 2 + (j - i)
+
+
+def tri_pack(G: np.ndarray) -> np.ndarray:
+    d = G.shape[0]
+    return G[np.triu_indices(d)]
+
+
+def tri_unpack(T: np.ndarray, d: int) -> np.ndarray:
+    G = np.zeros((d, d), dtype=T.dtype)
+    iu = np.triu_indices(d)
+    G[iu] = T
+    G.T[iu] = T
+    return G

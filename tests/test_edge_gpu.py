@@ -255,3 +255,42 @@ def test_pca_stream_fit_requires_every_cell(ffi, ctx):
     assert e.value.code == -1
     ps.free()
     m.free()
+
+
+def test_bulk_staged_row_reduce_irregular_long_rows(ffi, ctx):
+    """K1 in its cp.async.bulk form (lines of >= 128 stored entries on average): rows shorter, equal to and longer than
+    the 2048-value staging tile, empty rows, rows that straddle tile and CTA boundaries — sums bit-exact on integer data,
+    and the range / sign / integrality flags it feeds to the fixed-point moments must lead to the oracle's per-gene
+    statistics after normalise + log1p."""
+    rng = np.random.default_rng(77)
+    m = 9000
+    lens = [0, 1, 3, 127, 128, 2047, 2048, 2049, 4096, 4100, 0, 0, 6000, 5, 8999, 9000] + list(rng.integers(0, 6000, 150))
+    n = len(lens)
+    rows, cols, vals = [], [], []
+    for r, ln in enumerate(lens):
+        c = np.sort(rng.choice(m, size=int(ln), replace=False))
+        rows.append(np.full(c.size, r)), cols.append(c), vals.append(rng.integers(1, 40, c.size).astype(np.float32))
+    a = sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(n, m), dtype=np.float32)
+    a.sort_indices()
+    assert a.nnz / n >= 128
+    o = O.Compressed.from_scipy(a)
+    mt = ffi.DeviceMatrix.from_scipy(ctx, a)
+    np.testing.assert_array_equal(mt.sum(ffi.ROW), O.sum_(o, O.ROW))
+    np.testing.assert_array_equal(mt.number(ffi.ROW), O.number(o, O.ROW))
+    mn, mx = mt.min_max(ffi.ROW)
+    omn, omx = O.min_max(o, O.ROW)
+    np.testing.assert_array_equal(mn, omn), np.testing.assert_array_equal(mx, omx)
+    np.testing.assert_array_equal(mt.sum(ffi.COLUMN), O.sum_(o, O.COLUMN))          # exact fixed-point path (integer data)
+    mt.normalize_total_inplace(1e4, ffi.ROW)
+    mt.log1p_inplace()
+    ol = O.log1p(O.normalize_total(o, 1e4, O.ROW))
+    close(mt.sum(ffi.ROW), O.sum_(ol, O.ROW), rtol=1e-6)
+    close_compact_variance(mt.variance(ffi.COLUMN), ol, O.COLUMN)
+    # fractional / negative data must raise the flags (no fixed-point path): results still match the oracle
+    b = a.copy().astype(np.float64)
+    b.data = b.data * 0.37 - 3.0
+    mb = ffi.DeviceMatrix.from_scipy(ctx, b.astype(np.float32))
+    ob = O.Compressed.from_scipy(b.astype(np.float32))
+    close(mb.sum(ffi.ROW), O.sum_(ob, O.ROW), rtol=1e-6)
+    close(mb.variance(ffi.COLUMN), O.variance(ob, O.COLUMN), rtol=1e-5, atol=1e-9)
+    mt.free(), mb.free()

@@ -142,6 +142,65 @@ def test_sharded_gene_moments_are_bit_identical_and_match_oracle():
     assert np.all(np.abs(var1 - want) <= 1e-5 * want + 4e-7 * ex2)
 
 
+def _worker_gram(rank, world, port, q):
+    """The PCA exchange of a row-sharded job restated on the CPU: global per-gene moments (allreduce 1), each rank's
+    Gram matrix of its standardised rows, packed upper triangle summed over ranks (allreduce 2), replicated eigensolve."""
+    import torch.distributed as dist
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    from singlerust_b200 import synth
+    from singlerust_b200.parallel import shard_rows, tri_index, tri_pack, tri_unpack
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, m, d, k = 500, 120, 40, 4
+    thr, amp = synth.gene_tables(m, seed=5, mean_density=0.3)
+    a, b = shard_rows(n, world, rank)
+    shard = O.synth_csr(0x5EED0004, b - a, m, thr, amp, row0=a, skew=True)
+    ln = O.log1p(O.normalize_total(shard, 1e4, O.ROW))
+    sel = np.arange(d, dtype=np.uint64)
+    X = O.densify_selected(ln, np.arange(b - a, dtype=np.uint64), sel)
+    mom = torch.from_numpy(np.stack([X.sum(axis=0), (X * X).sum(axis=0)]))
+    dist.all_reduce(mom, op=dist.ReduceOp.SUM)
+    mean = mom[0].numpy() / n
+    std = np.sqrt(mom[1].numpy() / n - mean * mean)
+    Z = (X - mean) / std
+    T = torch.from_numpy(tri_pack(Z.T @ Z))
+    assert T.numel() == d * (d + 1) // 2 and tri_index(3, 7, d) == int(np.flatnonzero((np.triu_indices(d)[0] == 3) & (np.triu_indices(d)[1] == 7))[0])
+    dist.all_reduce(T, op=dist.ReduceOp.SUM)
+    G = tri_unpack(T.numpy(), d)
+    w, V = np.linalg.eigh(G)
+    if rank == 0:
+        q.put((G, w[::-1][:k] / np.trace(G), V[:, ::-1][:, :k]))
+    dist.destroy_process_group()
+
+
+def test_sharded_gram_triangle_exchange_matches_oracle_pca():
+    """world_size 2 (gloo): the packed-triangle Gram exchange reproduces the whole-matrix PCA of the oracle."""
+    import torch.multiprocessing as mp
+    from oracle import oracle as O
+    from oracle import pca_oracle as P
+    from singlerust_b200 import synth
+    from tests._util import sign_align
+    out = {}
+    for world, port in ((1, 29631), (2, 29633)):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker_gram, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        out[world] = q.get(timeout=120)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    np.testing.assert_allclose(out[2][0], out[1][0], rtol=1e-12, atol=1e-9)
+    thr, amp = synth.gene_tables(120, seed=5, mean_density=0.3)
+    whole = O.log1p(O.normalize_total(O.synth_csr(0x5EED0004, 500, 120, thr, amp, skew=True), 1e4, O.ROW))
+    want = P.pca_pipeline(whole, 40, 4, selection=np.arange(40, dtype=np.uint64))
+    np.testing.assert_allclose(out[2][1], want["explained_variance_ratio"], rtol=1e-9)
+    np.testing.assert_allclose(sign_align(out[2][2], want["components"]), want["components"], atol=1e-8)
+
+
 def test_filter_mask_host_logic_matches_oracle_all_nine_arms():
     """create_filter_mask / calculate_percentiles (processing/mod.rs:32-83, 148-174): host logic vs the arm-by-arm oracle."""
     from oracle import filter_oracle as FO

@@ -1,7 +1,8 @@
 """NumPy twin of csrc/eig.cu: chfsi_topk — the same flow, constants and update rules, used to validate the algorithm on
 spectra a GPU box is not needed for (tests/test_chfsi_twin.py) and to explore tunables before spending GPU time.
 
-    bounds (L Krylov steps, CGS2) -> [filter degree m (amplification of the top capped at 1e8) + CholeskyQR2] x R
+    bounds (L = 24 Krylov steps, CGS2) -> [filter degree m (amplification of the top capped at 1e8, trimmed to the
+    degree that reaches the target in R rounds) + CholeskyQR2] x R
     -> Rayleigh-Ritz -> residuals of the top k -> new cut / bounds -> ...            (at most 6 outer rounds)
 """
 from __future__ import annotations
@@ -45,10 +46,10 @@ def krylov_bounds(C, rng, L):
 
 
 def block_width(d, k):
-    return min(d // 4, ((max(3 * k, k + 96) + 63) // 64) * 64)
+    return min(d // 4, ((max(3 * k, k + 96) + 31) // 32) * 32)
 
 
-def chfsi_topk(C, k, seed=0, L=40, target=1e11, tol=1e-11, b=None, log=None):
+def chfsi_topk(C, k, seed=0, L=24, target=1e11, tol=1e-11, b=None, log=None):
     """Returns (eigenvalues ascending, eigenvectors, stats) or None where the CUDA code would fall back to syevd."""
     rng = np.random.default_rng(seed)
     d = C.shape[0]
@@ -87,6 +88,8 @@ def chfsi_topk(C, k, seed=0, L=40, target=1e11, tol=1e-11, b=None, log=None):
         amp = np.cosh(m * np.arccosh(xk))
         R = int(np.ceil(np.log(target) / np.log(max(amp, 1.0001))))
         R = max(1, min(R, 3 if outer == 0 else MAX_ROUNDS))
+        # the smallest degree that reaches the target in exactly R rounds (eig.cu: m_use)
+        m = max(2, min(m, int(np.ceil(np.arccosh(target ** (1.0 / R)) / np.arccosh(xk)))))
         if stats["block_products"] + R * m > MAX_PRODUCTS:
             return None  # work budget: costlier than the syevd it replaces
         for _ in range(R):
