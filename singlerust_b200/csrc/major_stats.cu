@@ -158,14 +158,17 @@ __global__ void __launch_bounds__(256) major_reduce_kernel(const int64_t *__rest
 // Every consumer warp waits for and releases every tile exactly once, in order (rows may span tiles).
 // ---------------------------------------------------------------------------------------------------------------------
 namespace k1b {
-constexpr int TILE = 2048, STAGES = 4, CONSUMERS = 2, THREADS = 32 * (1 + CONSUMERS);
+constexpr int TILE = 2048, STAGES = 4;
 }
 
-__global__ void __launch_bounds__(k1b::THREADS) major_sum_bulk_kernel(const int64_t *__restrict__ off, const float *__restrict__ val,
+template <int CONSUMERS>
+__global__ void __launch_bounds__(32 * (1 + CONSUMERS)) major_sum_bulk_kernel(const int64_t *__restrict__ off, const float *__restrict__ val,
                                                                       uint64_t nmajor, uint32_t rows_per_cta, double *__restrict__ o_sum,
                                                                       double *__restrict__ o_max, double *__restrict__ o_min,
                                                                       uint32_t *__restrict__ flags) {
     using namespace k1b;
+    constexpr int THREADS = 32 * (1 + CONSUMERS);
+    (void)THREADS;
     __shared__ __align__(128) float tile[STAGES][TILE];
     __shared__ __align__(8) uint64_t bars[2 * STAGES];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(k1b::THREADS) major_sum_bulk_kernel(const int6
     for (uint64_t r = r0 + cw; r < r1; r += CONSUMERS) {
         const int64_t a = off[r], b = off[r + 1];
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        uint32_t orbits = 0, maxab = 0, minab1 = 0xFFFFFFFFu, nonint = 0;
+        uint32_t orbits = 0, maxab = 0, minab1 = 0xFFFFFFFFu, fracbits = 0;
         int64_t pos = a;
         while (pos < b) {
             const uint32_t t = (uint32_t)((pos - base) / TILE);
@@ -218,35 +221,37 @@ __global__ void __launch_bounds__(k1b::THREADS) major_sum_bulk_kernel(const int6
             const int e = (int)(min(b, tile_lo + TILE) - tile_lo);
             const float *tp = tile[t % STAGES];
             int i = (int)(pos - tile_lo) + (int)lane;
-#define SRB_K1_TRACK(V)                                                       \
-    do {                                                                      \
-        const uint32_t bits = __float_as_uint(V), ab = bits & 0x7FFFFFFFu;    \
-        orbits |= bits;                                                       \
-        maxab = max(maxab, ab);                                               \
-        minab1 = min(minab1, ab - 1u);                                        \
-        nonint |= (uint32_t)((V) != truncf(V));                               \
+            // range / sign / finiteness / integrality on the raw bit patterns, two elements per 3-input instruction
+            // (LOP3, VIMNMX3): |v| = bits & 0x7FFFFFFF; zeros wrap to 0xFFFFFFFF in (|v| - 1) and drop out of the minimum;
+            // v - trunc(v) has a non-zero pattern exactly for fractions, NaN and inf
+#define SRB_K1_PAIR(VA, VB)                                                                              \
+    do {                                                                                                 \
+        const uint32_t ba = __float_as_uint(VA), bb = __float_as_uint(VB);                               \
+        const uint32_t aa = ba & 0x7FFFFFFFu, ab = bb & 0x7FFFFFFFu;                                     \
+        orbits |= ba | bb;                                                                               \
+        maxab = __vimax3_u32(maxab, aa, ab);                                                             \
+        minab1 = __vimin3_u32(minab1, aa - 1u, ab - 1u);                                                 \
+        fracbits |= __float_as_uint((VA) - truncf(VA)) | __float_as_uint((VB) - truncf(VB));             \
     } while (0)
             for (; i + 96 < e; i += 128) {
                 const float v0 = tp[i], v1 = tp[i + 32], v2 = tp[i + 64], v3 = tp[i + 96];
-                SRB_K1_TRACK(v0);
-                SRB_K1_TRACK(v1);
-                SRB_K1_TRACK(v2);
-                SRB_K1_TRACK(v3);
+                SRB_K1_PAIR(v0, v1);
+                SRB_K1_PAIR(v2, v3);
                 s0 += (double)v0, s1 += (double)v1, s2 += (double)v2, s3 += (double)v3;
             }
             for (; i < e; i += 32) {
                 const float v0 = tp[i];
-                SRB_K1_TRACK(v0);
+                SRB_K1_PAIR(v0, v0);
                 s0 += (double)v0;
             }
-#undef SRB_K1_TRACK
+#undef SRB_K1_PAIR
             pos = tile_lo + e;
         }
         const double sum = warp_sum((s0 + s1) + (s2 + s3));
         maxab = __reduce_max_sync(0xffffffffu, maxab);
         minab1 = __reduce_min_sync(0xffffffffu, minab1);
         orbits = __reduce_or_sync(0xffffffffu, orbits);
-        nonint = __reduce_or_sync(0xffffffffu, nonint);
+        const uint32_t nonint = (__reduce_or_sync(0xffffffffu, fracbits) & 0x7FFFFFFFu) ? 1u : 0u;
         if (lane == 0) {
             o_sum[r] = sum;
             o_max[r] = (double)__uint_as_float(maxab);
@@ -303,8 +308,19 @@ void major_sum_absmax(srb_mat *m) {
         uint64_t rpc = (n + (uint64_t)c->sm_count * 28 - 1) / ((uint64_t)c->sm_count * 28);
         rpc = std::max<uint64_t>(16, std::min<uint64_t>(rpc, 4096));
         const unsigned grid = (unsigned)((n + rpc - 1) / rpc);
-        SRB_LAUNCH(major_sum_bulk_kernel, grid, k1b::THREADS, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
-                   m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
+        static const int consumers = [] {
+            const char *e = getenv("SRB_K1_CONSUMERS");
+            return e ? atoi(e) : 2;
+        }();
+        if (consumers == 4)
+            SRB_LAUNCH(major_sum_bulk_kernel<4>, grid, 160, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
+                       m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
+        else if (consumers == 3)
+            SRB_LAUNCH(major_sum_bulk_kernel<3>, grid, 128, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
+                       m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
+        else
+            SRB_LAUNCH(major_sum_bulk_kernel<2>, grid, 96, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
+                       m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
     } else {
         launch_major<MODE_SUM_ABSMAX>(m, m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(),
                                       m->major.flags->as<uint32_t>());

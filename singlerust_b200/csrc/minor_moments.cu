@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -144,11 +145,15 @@ struct FusedParams {
 // ---------------------------------------------------------------------------------------------------
 // (A) fused exact kernel
 // ---------------------------------------------------------------------------------------------------
-template <typename VTI, typename VTO, bool WRITE, bool PIPE>
+template <typename VTI, typename VTO, bool WRITE>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const FusedParams p) {
+    // bins: 4 words per gene, INTERLEAVED [sum_lo | sq_lo | sq_mid | packed(count:14, sum_hi:12, sq_hi:6)] so that the four
+    // atomics of an entry share one base address (immediate offsets), addressed in the shared window directly (32-bit
+    // addresses, atom.shared: the generic-pointer form recomputed the window base per entry — SASS: S2UR/UMOV/ULEA + 2 IMAD)
     extern __shared__ uint32_t bins[];
     const uint32_t W = p.W;
-    uint32_t *s_sum = bins, *s_sqlo = bins + W, *s_sqmid = bins + 2 * (size_t)W, *s_pack = bins + 3 * (size_t)W;
+    uint32_t sbase = (uint32_t)__cvta_generic_to_shared(bins);
+    asm volatile("" : "+r"(sbase));  // opaque: keeps the compiler from re-deriving the window base (3 uniform ops) per entry
     for (uint32_t i = threadIdx.x; i < 4 * W; i += kFusedThreads) bins[i] = 0;
     __syncthreads();
 
@@ -164,50 +169,66 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
     const VTI *vin = reinterpret_cast<const VTI *>(p.vin);
     VTO *vout = reinterpret_cast<VTO *>(p.vout);  // may alias vin (in-place): same thread, same element
 
-    const bool has_scale = p.scale != nullptr;
-    const bool lg = p.do_log1p != 0;
-
     // Memory-level parallelism: the row's segment bounds are fetched one row ahead and the nnz are read in batches of
     // kBatch independent 128-byte warp loads per array before any of them is consumed (the ncu source view of the first
     // version showed ~75 % of the stall samples on the first use of the loaded value / index).
+    // The transform flags are uniform for the launch; the row loop is instantiated once per combination (SCALE: 0 none,
+    // 1 per row, 2 per column; LG) so that no flag is tested and no scale converted per entry (with the inline-asm atomics
+    // the compiler no longer unswitches the loop by itself).
     constexpr int kBatch = 8;
     auto seg_lo = [&](uint64_t r) { return (s == 0) ? p.off[r] : p.splits[(uint64_t)(s - 1) * p.nmajor + r]; };
     auto seg_hi = [&](uint64_t r) { return (s == p.S - 1) ? p.off[r + 1] : p.splits[(uint64_t)s * p.nmajor + r]; };
-    uint64_t r = r0 + warp;
-    int64_t a_next = 0, b_next = 0;
-    if (r < r1) a_next = seg_lo(r), b_next = seg_hi(r);
-    for (; r < r1; r += kFusedThreads / 32) {
-        const int64_t a = a_next, b = b_next;
-        const uint64_t rn = r + kFusedThreads / 32;
-        if (rn < r1) a_next = seg_lo(rn), b_next = seg_hi(rn);
-        const double sc_row = (has_scale && p.scale_major) ? p.scale[r] : 1.0;
-        // 32-bit offsets relative to the segment start keep the address arithmetic to one IMAD.WIDE per access
-        const uint32_t *ip = p.idx + a;
-        const VTI *vp = vin + a;
-        VTO *op = vout + a;
-        const int len = (int)(b - a);
-        auto consume = [&](uint32_t c, VTI v, int k) {
-            const double sc = (has_scale && !p.scale_major) ? p.scale[c] : sc_row;
-            const VTO x = Xform<VTO>::apply(v, sc, has_scale, lg);
-            if (WRITE) op[k] = x;
-            uint32_t q;
-            if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
-            else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
-            const uint32_t g = c - col_lo;
-            const uint32_t o1 = atomicAdd(&s_sum[g], q);
-            const unsigned long long q2 = (unsigned long long)q * q;
-            const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
-            const uint32_t o2 = atomicAdd(&s_sqlo[g], l);
-            uint32_t c1, add3, c3, t0;
-            // carries through add.cc / addc instead of compare + select
-            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c1) : "r"(o1), "r"(q));
-            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t0), "=r"(add3) : "r"(o2), "r"(l), "r"(h));
-            const uint32_t o3 = atomicAdd(&s_sqmid[g], add3);
-            asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c3) : "r"(o3), "r"(add3));
-            atomicAdd(&s_pack[g], (1u << 18) + c1 * 64u + c3);
-        };
-        if (!PIPE) {
-            for (int k0 = lane; k0 < len; k0 += 32 * kBatch) {
+    auto rows = [&](auto scale_tag, auto lg_tag) {
+        constexpr int SCALE = decltype(scale_tag)::value;
+        constexpr bool LG = decltype(lg_tag)::value;
+        uint64_t r = r0 + warp;
+        int64_t a_next = 0, b_next = 0;
+        if (r < r1) a_next = seg_lo(r), b_next = seg_hi(r);
+        for (; r < r1; r += kFusedThreads / 32) {
+            const int64_t a = a_next, b = b_next;
+            const uint64_t rn = r + kFusedThreads / 32;
+            if (rn < r1) a_next = seg_lo(rn), b_next = seg_hi(rn);
+            const double sc_row = SCALE == 1 ? p.scale[r] : 1.0;
+            const VTO sc_row_t = (VTO)sc_row;  // f32 pipeline: the scale is rounded once to f32 (Xform<float>)
+            // 32-bit offsets relative to the segment start keep the address arithmetic to one IMAD.WIDE per access
+            const uint32_t *ip = p.idx + a;
+            const VTI *vp = vin + a;
+            VTO *op = vout + a;
+            const int len = (int)(b - a);
+            auto consume = [&](uint32_t c, VTI v, int k) {
+                VTO x = (VTO)v;
+                if (SCALE == 1) x *= sc_row_t;
+                if (SCALE == 2) x *= (VTO)p.scale[c];
+                if (LG) x = sizeof(VTO) == 4 ? (VTO)log1pf((float)x) : (VTO)log1p((double)x);
+                if (WRITE) op[k] = x;
+                uint32_t q;
+                if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
+                else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
+                const uint32_t ga = sbase + (c - col_lo) * 16u;
+                uint32_t o1, o2, o3;
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o1) : "r"(ga), "r"(q) : "memory");
+                const unsigned long long q2 = (unsigned long long)q * q;
+                const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
+                asm volatile("atom.shared.add.u32 %0, [%1+4], %2;" : "=r"(o2) : "r"(ga), "r"(l) : "memory");
+                uint32_t c1, add3, c3, t0;
+                // carries through add.cc / addc instead of compare + select
+                asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c1) : "r"(o1), "r"(q));
+                asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t0), "=r"(add3) : "r"(o2), "r"(l), "r"(h));
+                asm volatile("atom.shared.add.u32 %0, [%1+8], %2;" : "=r"(o3) : "r"(ga), "r"(add3) : "memory");
+                asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c3) : "r"(o3), "r"(add3));
+                asm volatile("red.shared.add.u32 [%0+12], %1;" ::"r"(ga), "r"((1u << 18) + c1 * 64u + c3) : "memory");
+            };
+            int k0 = lane;
+            // whole batches: every lane of the warp is in range, no predicate per entry
+            for (; k0 - lane + 32 * kBatch <= len; k0 += 32 * kBatch) {
+                uint32_t cc[kBatch];
+                VTI vv[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) cc[u] = ip[k0 + 32 * u], vv[u] = vp[k0 + 32 * u];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) consume(cc[u], vv[u], k0 + 32 * u);
+            }
+            if (k0 < len) {  // the ragged tail of the segment
                 uint32_t cc[kBatch];
                 VTI vv[kBatch];
 #pragma unroll
@@ -223,50 +244,36 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
                     if (k < len) consume(cc[u], vv[u], k);
                 }
             }
+        }
+    };
+    {
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using I2 = std::integral_constant<int, 2>;
+        const bool lg = p.do_log1p != 0;
+        if (p.scale == nullptr) {
+            if (lg) rows(I0{}, std::true_type{}); else rows(I0{}, std::false_type{});
+        } else if (p.scale_major) {
+            if (lg) rows(I1{}, std::true_type{}); else rows(I1{}, std::false_type{});
         } else {
-            // register double buffer: the next half-batch of loads is in flight while the current one runs its atomics
-            constexpr int kHalf = kBatch / 2;
-            uint32_t cc[kHalf], cn[kHalf];
-            VTI vv[kHalf], vn[kHalf];
-            int k0 = lane;
-#pragma unroll
-            for (int u = 0; u < kHalf; ++u) {
-                const int k = k0 + 32 * u;
-                cc[u] = k < len ? ip[k] : 0u;
-                vv[u] = k < len ? vp[k] : (VTI)0;
-            }
-            for (; k0 < len; k0 += 32 * kHalf) {
-                const int kn = k0 + 32 * kHalf;
-#pragma unroll
-                for (int u = 0; u < kHalf; ++u) {
-                    const int k = kn + 32 * u;
-                    cn[u] = k < len ? ip[k] : 0u;
-                    vn[u] = k < len ? vp[k] : (VTI)0;
-                }
-#pragma unroll
-                for (int u = 0; u < kHalf; ++u) {
-                    const int k = k0 + 32 * u;
-                    if (k < len) consume(cc[u], vv[u], k);
-                }
-#pragma unroll
-                for (int u = 0; u < kHalf; ++u) cc[u] = cn[u], vv[u] = vn[u];
-            }
+            if (lg) rows(I2{}, std::true_type{}); else rows(I2{}, std::false_type{});
         }
     }
     __syncthreads();
     unsigned long long *acc = p.acc;
     const uint64_t M = p.nminor;
     for (uint32_t g = threadIdx.x; g < W; g += kFusedThreads) {
-        const uint32_t pk = s_pack[g];
+        const uint4 bin = reinterpret_cast<const uint4 *>(bins)[g];  // sum_lo, sq_lo, sq_mid, packed
+        const uint32_t pk = bin.w;
         const uint32_t cnt = pk >> 18;
         if (cnt == 0) continue;
         const uint64_t col = (uint64_t)col_lo + g;
         atomicAdd(&acc[col], (unsigned long long)cnt);
-        atomicAdd(&acc[M + col], (unsigned long long)s_sum[g]);
+        atomicAdd(&acc[M + col], (unsigned long long)bin.x);
         const uint32_t sh = (pk >> 6) & 0xFFFu;
         if (sh) atomicAdd(&acc[2 * M + col], (unsigned long long)sh);
-        atomicAdd(&acc[3 * M + col], (unsigned long long)s_sqlo[g]);
-        atomicAdd(&acc[4 * M + col], (unsigned long long)s_sqmid[g]);
+        atomicAdd(&acc[3 * M + col], (unsigned long long)bin.y);
+        atomicAdd(&acc[4 * M + col], (unsigned long long)bin.z);
         const uint32_t qh = pk & 63u;
         if (qh) atomicAdd(&acc[5 * M + col], (unsigned long long)qh);
     }
@@ -484,20 +491,13 @@ static bool exact_path_ok(srb_mat *m, const Buf &range, bool pending, bool lg, i
 template <typename VTI, typename VTO>
 static void launch_fused(srb_mat *m, const FusedParams &p, bool write, unsigned grid, size_t smem) {
     cudaStream_t s = m->ctx->stream;
-    static int pipe = -1;
-    if (pipe < 0) {
-        const char *e = getenv("SRB_FUSED_PIPE");
-        pipe = (e && e[0] == '1') ? 1 : 0;
-    }
-#define SRB_FUSED_GO(W, P)                                                                                                          \
-    do {                                                                                                                            \
-        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, W, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, W, P>), grid, kFusedThreads, smem, s, p);                                          \
+#define SRB_FUSED_GO(W)                                                                                                          \
+    do {                                                                                                                         \
+        SRB_CUDA(cudaFuncSetAttribute(fused_exact_kernel<VTI, VTO, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        SRB_LAUNCH((fused_exact_kernel<VTI, VTO, W>), grid, kFusedThreads, smem, s, p);                                          \
     } while (0)
-    if (write && pipe) SRB_FUSED_GO(true, true);
-    else if (write) SRB_FUSED_GO(true, false);
-    else if (pipe) SRB_FUSED_GO(false, true);
-    else SRB_FUSED_GO(false, false);
+    if (write) SRB_FUSED_GO(true);
+    else SRB_FUSED_GO(false);
 #undef SRB_FUSED_GO
 }
 

@@ -14,7 +14,6 @@
 #include <cmath>
 #include <cstdlib>
 
-#include "bulk.cuh"
 #include "common.cuh"
 
 namespace srb {
@@ -79,6 +78,8 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
 // 16-byte stores; step 2 overwrites the stored entries with 2-byte scattered stores — they hit the lines step 1 just
 // put into L2, so DRAM sees each line once. __syncwarp() orders the two steps inside the warp.
 // HBM: 8 B/nnz in, 4*dpad B/row out.
+// (A cp.async.bulk-staged variant — tile ring, 8 consumer warps per tile, row lookup by binary search — was measured in
+// round 2 at 12.5 ms against 4.5 ms for this kernel: 70 instructions per entry and a barrier per tile; it was removed.)
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const uint16_t *__restrict__ lut,
@@ -185,122 +186,6 @@ __global__ void __launch_bounds__(256) densify_panels_pipe_kernel(const int64_t 
             for (int u = 0; u < kBatch; ++u) cc[u] = cn[u], vv[u] = vn[u];
         }
         __syncwarp();
-    }
-}
-
-// K6, bulk-staged form (f32 values): the (index, value) run of a CTA's rows is streamed tile by tile (2048 entries: 8 KB +
-// 8 KB) into a 4-stage shared-memory ring by cp.async.bulk (one producer thread), decoupling the HBM latency from the
-// dependent chain index -> LUT -> (shift, 1 / sd) -> store that made the warp-per-row kernel latency-bound (issue slots 29 %
-// busy). 8 consumer warps work on one tile together: (A) the rows that START in the tile get their implicit-zero constants
-// (16-byte stores, one warp per row), a named barrier, (B) every thread takes 8 consecutive entries, finds their row by a
-// binary search of the CTA's row offsets (shared memory) and overwrites the selected ones with 2-byte stores that hit the
-// lines step A just put into L2.
-namespace k6b {
-constexpr int TILE = 2048, STAGES = 4, CWARPS = 8, THREADS = 32 * (1 + CWARPS), MAX_ROWS = 64;
-constexpr size_t SMEM = (size_t)STAGES * TILE * 8;
-}
-__global__ void __launch_bounds__(k6b::THREADS) densify_panels_bulk_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
-                                                                          const float *__restrict__ val, const uint16_t *__restrict__ lut,
-                                                                          const float2 *__restrict__ shis, const __half *__restrict__ zc_h,
-                                                                          const __half *__restrict__ zc_l, uint64_t nrows, uint32_t rows_per_cta,
-                                                                          uint32_t dpad, __half *__restrict__ Xh, __half *__restrict__ Xl) {
-    using namespace k6b;
-    extern __shared__ __align__(128) uint8_t k6_smem[];  // [idx ring | value ring] (dynamic: 64 KB)
-    uint32_t(*s_idx)[TILE] = reinterpret_cast<uint32_t(*)[TILE]>(k6_smem);
-    float(*s_val)[TILE] = reinterpret_cast<float(*)[TILE]>(k6_smem + (size_t)STAGES * TILE * 4);
-    __shared__ __align__(8) uint64_t bars[2 * STAGES];
-    __shared__ int64_t s_off[MAX_ROWS + 1];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
-    if (r0 >= nrows) return;
-    const uint32_t nr = (uint32_t)min((uint64_t)rows_per_cta, nrows - r0);
-    for (uint32_t i = threadIdx.x; i <= nr; i += THREADS) s_off[i] = off[r0 + i];
-    const uint32_t full0 = bulk::smem_u32(&bars[0]), empty0 = bulk::smem_u32(&bars[STAGES]);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) bulk::mbar_init(full0 + 8 * s, 1), bulk::mbar_init(empty0 + 8 * s, CWARPS);
-        bulk::mbar_init_fence();
-    }
-    __syncthreads();
-    const int64_t a0 = s_off[0], b1 = s_off[nr];
-    const int64_t base = a0 & ~(int64_t)3;
-    const uint32_t ntiles = (uint32_t)((b1 - base + TILE - 1) / TILE);
-    if (warp == 0) {
-        if (lane == 0) {
-            for (uint32_t t = 0; t < ntiles; ++t) {
-                const uint32_t s = t % STAGES;
-                bulk::mbar_wait(empty0 + 8 * s, ((t / STAGES) & 1) ^ 1);
-                const int64_t lo = base + (int64_t)t * TILE;
-                const uint32_t n = (uint32_t)min((int64_t)TILE, (b1 - lo + 3) & ~(int64_t)3);
-                bulk::mbar_arrive_expect_tx(full0 + 8 * s, 8 * n);
-                bulk::copy_g2s(bulk::smem_u32(&s_idx[s][0]), idx + lo, 4 * n, full0 + 8 * s);
-                bulk::copy_g2s(bulk::smem_u32(&s_val[s][0]), val + lo, 4 * n, full0 + 8 * s);
-            }
-        }
-        return;
-    }
-    const uint32_t cw = warp - 1, ct = threadIdx.x - 32;  // consumer warp / thread index
-    const uint32_t nvec = dpad / 8;
-    const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
-    auto fill_row = [&](uint32_t lr) {
-        uint4 *oh = reinterpret_cast<uint4 *>(Xh + (r0 + lr) * dpad), *ol = reinterpret_cast<uint4 *>(Xl + (r0 + lr) * dpad);
-        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
-    };
-    if (ntiles == 0) {  // no stored entry in any of the CTA's rows
-        for (uint32_t lr = cw; lr < nr; lr += CWARPS) fill_row(lr);
-        return;
-    }
-    uint32_t fill_next = 0;  // rows before fill_next have their constants (identical in every consumer thread)
-    for (uint32_t t = 0; t < ntiles; ++t) {
-        const uint32_t s = t % STAGES;
-        const int64_t lo = base + (int64_t)t * TILE, hi = (t + 1 == ntiles) ? INT64_MAX : lo + TILE;
-        // (A) rows whose first position falls into this tile (empty rows included; the last tile takes the rest)
-        uint32_t fill_end = fill_next;
-        while (fill_end < nr && s_off[fill_end] < hi) ++fill_end;
-        for (uint32_t lr = fill_next + cw; lr < fill_end; lr += CWARPS) fill_row(lr);
-        fill_next = fill_end;
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * CWARPS) : "memory");
-        bulk::mbar_wait(full0 + 8 * s, (t / STAGES) & 1);
-        // (B) 8 consecutive entries per thread
-        const int64_t p0 = lo + (int64_t)ct * 8;
-        const int64_t pend = min(b1, lo + TILE);
-        if (p0 < pend && p0 + 8 > a0) {
-            // row of the first entry: the last lr with s_off[lr] <= max(p0, a0)
-            const int64_t pf = max(p0, a0);
-            uint32_t lo_r = 0, hi_r = nr;  // invariant: s_off[lo_r] <= pf < s_off[hi_r]
-            while (hi_r - lo_r > 1) {
-                const uint32_t mid = (lo_r + hi_r) >> 1;
-                if (s_off[mid] <= pf) lo_r = mid; else hi_r = mid;
-            }
-            uint32_t lr = lo_r;
-            int64_t row_end = s_off[lr + 1];
-            const uint4 ia = *reinterpret_cast<const uint4 *>(&s_idx[s][ct * 8]), ib = *reinterpret_cast<const uint4 *>(&s_idx[s][ct * 8 + 4]);
-            const float4 va = *reinterpret_cast<const float4 *>(&s_val[s][ct * 8]), vb = *reinterpret_cast<const float4 *>(&s_val[s][ct * 8 + 4]);
-            const uint32_t cc[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-            const float vv[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
-            uint32_t pp[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t p = p0 + u;
-                pp[u] = (p >= a0 && p < pend) ? (uint32_t)lut[cc[u]] : 0xFFFFu;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int64_t p = p0 + u;
-                if (p >= a0 && p < pend) {
-                    while (p >= row_end) row_end = s_off[(++lr) + 1];  // next non-empty row
-                    if (pp[u] != 0xFFFFu) {
-                        const float2 si = shis[pp[u]];
-                        const float z = (vv[u] - si.x) * si.y;
-                        const __half h = __float2half_rn(z);
-                        const size_t o = (size_t)(r0 + lr) * dpad + pp[u];
-                        Xh[o] = h;
-                        Xl[o] = __float2half_rn(z - __half2float(h));
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) bulk::mbar_arrive(empty0 + 8 * s);
     }
 }
 
@@ -569,18 +454,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             const char *e = getenv("SRB_DENSIFY_PIPE");
             pipe = (e && e[0] == '0') ? 0 : 1;  // default: register double-buffered variant (4.40 vs 4.68 ms at L)
         }
-        static const int bulk_on = [] {
-            const char *e = getenv("SRB_K6_BULK");
-            return (e && e[0] == '0') ? 0 : 1;
-        }();
-        if (m->vdtype == SRB_F32 && bulk_on && (double)m->st->nnz / (double)n >= 128.0) {
-            uint64_t rpc = (n + (uint64_t)c->sm_count * 24 - 1) / ((uint64_t)c->sm_count * 24);
-            rpc = std::max<uint64_t>(8, std::min<uint64_t>(rpc, k6b::MAX_ROWS));
-            SRB_CUDA(cudaFuncSetAttribute(densify_panels_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k6b::SMEM));
-            SRB_LAUNCH(densify_panels_bulk_kernel, (unsigned)((n + rpc - 1) / rpc), k6b::THREADS, k6b::SMEM, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(),
-                       m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, (uint32_t)rpc, dpad,
-                       Xh->as<__half>(), Xl->as<__half>());
-        } else if (m->vdtype == SRB_F32 && pipe) {
+        if (m->vdtype == SRB_F32 && pipe) {
             SRB_LAUNCH((densify_panels_pipe_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else if (m->vdtype == SRB_F32) {
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
