@@ -147,9 +147,12 @@ struct FusedParams {
 // ---------------------------------------------------------------------------------------------------
 template <typename VTI, typename VTO, bool WRITE>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const FusedParams p) {
-    // bins: 4 words per gene, INTERLEAVED [sum_lo | sq_lo | sq_mid | packed(count:14, sum_hi:12, sq_hi:6)] so that the four
-    // atomics of an entry share one base address (immediate offsets), addressed in the shared window directly (32-bit
-    // addresses, atom.shared: the generic-pointer form recomputed the window base per entry — SASS: S2UR/UMOV/ULEA + 2 IMAD)
+    // bins: 4 words per gene [sum_lo | sq_lo | sq_mid | packed(count:14, sum_hi:12, sq_hi:6)], stored in blocks of 32 genes
+    // x 4 word-rows of 128 bytes: word w of gene g sits at byte (g >> 5) * 512 + w * 128 + (g & 31) * 4. The four atomics of
+    // an entry share one base register (immediate offsets 0 / 128 / 256 / 384) and gene g still maps to bank g mod 32 (a
+    // gene-interleaved layout, 16 bytes per gene, put every atomic on 8 of the 32 banks: measured 5.6 instead of 4.3 ms).
+    // Addressed in the shared window directly (32-bit addresses, atom.shared): the generic-pointer form recomputed the window
+    // base per entry (SASS: S2UR / UMOV / ULEA + 2 IMAD).
     extern __shared__ uint32_t bins[];
     const uint32_t W = p.W;
     uint32_t sbase = (uint32_t)__cvta_generic_to_shared(bins);
@@ -204,19 +207,20 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
                 uint32_t q;
                 if (sizeof(VTO) == 4) q = __float2uint_rn((float)x * qsf);
                 else q = (uint32_t)min(__double2ull_rn((double)x * qs), 0xFFFFFFFFULL);
-                const uint32_t ga = sbase + (c - col_lo) * 16u;
+                const uint32_t g = c - col_lo;
+                const uint32_t ga = sbase + (g << 2) + (g >> 5) * 384u;
                 uint32_t o1, o2, o3;
                 asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o1) : "r"(ga), "r"(q) : "memory");
                 const unsigned long long q2 = (unsigned long long)q * q;
                 const uint32_t l = (uint32_t)q2, h = (uint32_t)(q2 >> 32);
-                asm volatile("atom.shared.add.u32 %0, [%1+4], %2;" : "=r"(o2) : "r"(ga), "r"(l) : "memory");
+                asm volatile("atom.shared.add.u32 %0, [%1+128], %2;" : "=r"(o2) : "r"(ga), "r"(l) : "memory");
                 uint32_t c1, add3, c3, t0;
                 // carries through add.cc / addc instead of compare + select
                 asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c1) : "r"(o1), "r"(q));
                 asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(t0), "=r"(add3) : "r"(o2), "r"(l), "r"(h));
-                asm volatile("atom.shared.add.u32 %0, [%1+8], %2;" : "=r"(o3) : "r"(ga), "r"(add3) : "memory");
+                asm volatile("atom.shared.add.u32 %0, [%1+256], %2;" : "=r"(o3) : "r"(ga), "r"(add3) : "memory");
                 asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(t0), "=r"(c3) : "r"(o3), "r"(add3));
-                asm volatile("red.shared.add.u32 [%0+12], %1;" ::"r"(ga), "r"((1u << 18) + c1 * 64u + c3) : "memory");
+                asm volatile("red.shared.add.u32 [%0+384], %1;" ::"r"(ga), "r"((1u << 18) + c1 * 64u + c3) : "memory");
             };
             int k0 = lane;
             // whole batches: every lane of the warp is in range, no predicate per entry
@@ -263,7 +267,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_exact_kernel(const Fus
     unsigned long long *acc = p.acc;
     const uint64_t M = p.nminor;
     for (uint32_t g = threadIdx.x; g < W; g += kFusedThreads) {
-        const uint4 bin = reinterpret_cast<const uint4 *>(bins)[g];  // sum_lo, sq_lo, sq_mid, packed
+        const uint32_t *bw = bins + (g >> 5) * 128u + (g & 31u);
+        const uint4 bin = make_uint4(bw[0], bw[32], bw[64], bw[96]);  // sum_lo, sq_lo, sq_mid, packed
         const uint32_t pk = bin.w;
         const uint32_t cnt = pk >> 18;
         if (cnt == 0) continue;

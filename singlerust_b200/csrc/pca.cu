@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__re
 }
 
 // default variant: register double buffer (SRB_DENSIFY_PIPE=0 selects the plain batched kernel above)
-template <typename VT>
-__global__ void __launch_bounds__(256) densify_panels_pipe_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
+template <typename VT, int kBatch>
+__global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const uint16_t *__restrict__ lut,
                                                              const float2 *__restrict__ shis,
                                                              const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
@@ -142,13 +142,15 @@ __global__ void __launch_bounds__(256) densify_panels_pipe_kernel(const int64_t 
     const uint64_t nwarps = (uint64_t)gridDim.x * 8;
     const uint32_t nvec = dpad / 8;  // uint4 = 8 halves
     const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
-    constexpr int kBatch = 4;
-    for (uint64_t r = warp; r < nrows; r += nwarps) {
-        const int64_t a = off[r], b = off[r + 1];
-        uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
-        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
-        __syncwarp();
-        __half *rh = Xh + r * dpad, *rl = Xl + r * dpad;
+    // the row bounds are fetched one row ahead and the first batch of (index, value) loads is issued BEFORE the 8 KB of
+    // implicit-zero constants are written, so neither the offset load nor the fill leaves the warp without loads in flight
+    uint64_t r = warp;
+    int64_t a_next = 0, b_next = 0;
+    if (r < nrows) a_next = off[r], b_next = off[r + 1];
+    for (; r < nrows; r += nwarps) {
+        const int64_t a = a_next, b = b_next;
+        const uint64_t rn = r + nwarps;
+        if (rn < nrows) a_next = off[rn], b_next = off[rn + 1];
         // software pipeline: the next batch of (index, value) loads is in flight while the current batch walks the
         // dependent chain index -> LUT -> (shift, 1/sd) -> store
         uint32_t cc[kBatch], cn[kBatch];
@@ -160,6 +162,10 @@ __global__ void __launch_bounds__(256) densify_panels_pipe_kernel(const int64_t 
             cc[u] = k < b ? idx[k] : 0xFFFFFFFFu;
             vv[u] = k < b ? (float)val[k] : 0.f;
         }
+        uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
+        for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
+        __syncwarp();
+        __half *rh = Xh + r * dpad, *rl = Xl + r * dpad;
         for (; k0 < b; k0 += 32 * kBatch) {
             const int64_t kn = k0 + 32 * kBatch;
 #pragma unroll
@@ -454,8 +460,14 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             const char *e = getenv("SRB_DENSIFY_PIPE");
             pipe = (e && e[0] == '0') ? 0 : 1;  // default: register double-buffered variant (4.40 vs 4.68 ms at L)
         }
-        if (m->vdtype == SRB_F32 && pipe) {
-            SRB_LAUNCH((densify_panels_pipe_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        static const int batch8 = [] {
+            const char *e = getenv("SRB_DENSIFY_BATCH");
+            return (e && atoi(e) == 8) ? 1 : 0;
+        }();
+        if (m->vdtype == SRB_F32 && pipe && batch8) {
+            SRB_LAUNCH((densify_panels_pipe_kernel<float, 8>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        } else if (m->vdtype == SRB_F32 && pipe) {
+            SRB_LAUNCH((densify_panels_pipe_kernel<float, 4>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else if (m->vdtype == SRB_F32) {
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
@@ -556,7 +568,7 @@ static void stream_densify(srb_pca_stream *ps, srb_mat *m, Buf &Xh, Buf &Xl) {
     if (!n) return;
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8 * 4);
     if (m->vdtype == SRB_F32)
-        SRB_LAUNCH((densify_panels_pipe_kernel<float>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        SRB_LAUNCH((densify_panels_pipe_kernel<float, 4>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
     else
         SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
 }
