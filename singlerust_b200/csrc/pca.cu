@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "bulk.cuh"
 #include "common.cuh"
 
 namespace srb {
@@ -78,8 +79,9 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
 // 16-byte stores; step 2 overwrites the stored entries with 2-byte scattered stores — they hit the lines step 1 just
 // put into L2, so DRAM sees each line once. __syncwarp() orders the two steps inside the warp.
 // HBM: 8 B/nnz in, 4*dpad B/row out.
-// (A cp.async.bulk-staged variant — tile ring, 8 consumer warps per tile, row lookup by binary search — was measured in
-// round 2 at 12.5 ms against 4.5 ms for this kernel: 70 instructions per entry and a barrier per tile; it was removed.)
+// (A first cp.async.bulk-staged variant in which 8 warps worked on one tile together — a barrier per tile, the row of an
+// entry found by binary search — took 12.5 ms against 4.5 ms for this kernel and was removed; the row-owning form that
+// replaced it is densify_panels_bulk_kernel below.)
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const uint16_t *__restrict__ lut,
@@ -193,6 +195,109 @@ __global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_
         }
         __syncwarp();
     }
+}
+
+// K6, bulk-staged form (f32 values, <= 32 768 genes, rows of >= 128 entries on average) — the structure that took K1 from
+// 0.69 to 0.88 of the HBM peak: the (index, value) run of a CTA's rows is streamed tile by tile (1024 entries: 4 KB + 4 KB)
+// into a 4-stage shared-memory ring by cp.async.bulk (one producer thread), and 4 consumer warps own whole rows: a warp
+// writes its row's implicit-zero constants (16-byte stores), then walks the row out of shared memory, lane-strided. The
+// selection test is a 4 KB bitmap in shared memory (93 % of the entries end there); only selected entries go on to the
+// LUT / (shift, 1 / sd) lookups and the two 2-byte stores, which hit the lines the fill just put into L2. Every consumer warp
+// waits for and releases every tile exactly once, in order (rows span tiles).
+namespace k6b {
+constexpr int TILE = 1024, STAGES = 4, MAX_GENES = 32768;
+}
+__global__ void sel_bitmap_kernel(const uint32_t *__restrict__ sel, uint64_t n_sel, uint32_t *__restrict__ bits) {
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_sel) atomicOr(&bits[sel[j] >> 5], 1u << (sel[j] & 31));
+}
+template <int CONSUMERS>
+__global__ void __launch_bounds__(32 * (1 + CONSUMERS)) densify_panels_bulk_kernel(
+    const int64_t *__restrict__ off, const uint32_t *__restrict__ idx, const float *__restrict__ val, const uint16_t *__restrict__ lut,
+    const uint32_t *__restrict__ selbits, const float2 *__restrict__ shis, const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
+    uint64_t nrows, uint32_t rows_per_cta, uint32_t dpad, __half *__restrict__ Xh, __half *__restrict__ Xl) {
+    using namespace k6b;
+    __shared__ __align__(128) uint32_t s_idx[STAGES][TILE];
+    __shared__ __align__(128) float s_val[STAGES][TILE];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES];
+    __shared__ uint32_t s_bits[MAX_GENES / 32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
+    if (r0 >= nrows) return;
+    const uint64_t r1 = min(r0 + (uint64_t)rows_per_cta, nrows);
+    for (uint32_t i = threadIdx.x; i < MAX_GENES / 32; i += blockDim.x) s_bits[i] = selbits[i];
+    const int64_t a0 = off[r0], b1 = off[r1];
+    const int64_t base = a0 & ~(int64_t)3;
+    const uint32_t ntiles = (uint32_t)((b1 - base + TILE - 1) / TILE);
+    const uint32_t full0 = bulk::smem_u32(&bars[0]), empty0 = bulk::smem_u32(&bars[STAGES]);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) bulk::mbar_init(full0 + 8 * s, 1), bulk::mbar_init(empty0 + 8 * s, CONSUMERS);
+        bulk::mbar_init_fence();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) {
+            for (uint32_t t = 0; t < ntiles; ++t) {
+                const uint32_t s = t % STAGES;
+                bulk::mbar_wait(empty0 + 8 * s, ((t / STAGES) & 1) ^ 1);
+                const int64_t lo = base + (int64_t)t * TILE;
+                const uint32_t n = (uint32_t)min((int64_t)TILE, (b1 - lo + 3) & ~(int64_t)3);
+                bulk::mbar_arrive_expect_tx(full0 + 8 * s, 8 * n);
+                bulk::copy_g2s(bulk::smem_u32(&s_idx[s][0]), idx + lo, 4 * n, full0 + 8 * s);
+                bulk::copy_g2s(bulk::smem_u32(&s_val[s][0]), val + lo, 4 * n, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+    const uint32_t cw = warp - 1;
+    const uint32_t nvec = dpad / 8;
+    const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
+    uint32_t t_cur = 0;
+    bool have = false;
+    auto release_until = [&](uint32_t t) {
+        while (t_cur < t) {
+            if (!have) bulk::mbar_wait(full0 + 8 * (t_cur % STAGES), (t_cur / STAGES) & 1);
+            __syncwarp();
+            if (lane == 0) bulk::mbar_arrive(empty0 + 8 * (t_cur % STAGES));
+            ++t_cur, have = false;
+        }
+    };
+    for (uint64_t r = r0 + cw; r < r1; r += CONSUMERS) {
+        const int64_t a = off[r], b = off[r + 1];
+        __half *rh = Xh + r * dpad, *rl = Xl + r * dpad;
+        {
+            uint4 *oh = reinterpret_cast<uint4 *>(rh), *ol = reinterpret_cast<uint4 *>(rl);
+            for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
+        }
+        __syncwarp();
+        int64_t pos = a;
+        while (pos < b) {
+            const uint32_t t = (uint32_t)((pos - base) / TILE);
+            release_until(t);
+            if (!have) bulk::mbar_wait(full0 + 8 * (t % STAGES), (t / STAGES) & 1), have = true;
+            const int64_t tile_lo = base + (int64_t)t * TILE;
+            const int e = (int)(min(b, tile_lo + TILE) - tile_lo);
+            const uint32_t *ti = s_idx[t % STAGES];
+            const float *tv = s_val[t % STAGES];
+            auto one = [&](int i) {
+                const uint32_t c = ti[i];
+                if ((s_bits[c >> 5] >> (c & 31)) & 1u) {
+                    const uint32_t p = lut[c];
+                    const float2 si = shis[p];
+                    const float z = (tv[i] - si.x) * si.y;
+                    const __half h = __float2half_rn(z);
+                    rh[p] = h;
+                    rl[p] = __float2half_rn(z - __half2float(h));
+                }
+            };
+            int i = (int)(pos - tile_lo) + (int)lane;
+            for (; i + 96 < e; i += 128) one(i), one(i + 32), one(i + 64), one(i + 96);
+            for (; i < e; i += 32) one(i);
+            pos = tile_lo + e;
+        }
+        __syncwarp();
+    }
+    release_until(ntiles);
 }
 
 // K7 (validation path): G += X^T X in fp64 on CUDA cores. 64x64 output tile per CTA, upper-triangular tiles only,
@@ -460,6 +565,19 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             const char *e = getenv("SRB_DENSIFY_PIPE");
             pipe = (e && e[0] == '0') ? 0 : 1;  // default: register double-buffered variant (4.40 vs 4.68 ms at L)
         }
+        static const int bulk_on = [] {
+            const char *e = getenv("SRB_K6_BULK");
+            return (e && e[0] == '0') ? 0 : 1;
+        }();
+        if (m->vdtype == SRB_F32 && bulk_on && M <= (uint64_t)k6b::MAX_GENES && (double)m->st->nnz / (double)n >= 128.0) {
+            Buf bits = dev_zeros(s, 4 * (k6b::MAX_GENES / 32));
+            SRB_LAUNCH(sel_bitmap_kernel, nb(n_sel), 256, 0, s, d_sel, n_sel, bits->as<uint32_t>());
+            uint64_t rpc = (n + (uint64_t)c->sm_count * 24 - 1) / ((uint64_t)c->sm_count * 24);
+            rpc = std::max<uint64_t>(16, std::min<uint64_t>(rpc, 256));
+            SRB_LAUNCH(densify_panels_bulk_kernel<4>, (unsigned)((n + rpc - 1) / rpc), 160, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(),
+                       m->values->as<float>(), lut16->as<uint16_t>(), bits->as<uint32_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n,
+                       (uint32_t)rpc, dpad, Xh->as<__half>(), Xl->as<__half>());
+        } else {
         static const int batch8 = [] {
             const char *e = getenv("SRB_DENSIFY_BATCH");
             return (e && atoi(e) == 8) ? 1 : 0;
@@ -472,6 +590,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
             SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        }
         }
     }
     SRB_TRACE("panels alloc + densify enqueue");
