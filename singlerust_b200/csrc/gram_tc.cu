@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(THREADS, 1) scores_tc_kernel(const __grid_cons
                                                                const __grid_constant__ CUtensorMap map_zl,
                                                                const __grid_constant__ CUtensorMap map_wh,
                                                                const __grid_constant__ CUtensorMap map_wl, uint64_t nrows,
-                                                               uint32_t kblocks, uint32_t k, double *__restrict__ scores) {
+                                                               uint32_t kblocks, uint32_t k, const double *__restrict__ bias,
+                                                               double *__restrict__ scores) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = base + S_STAGES * S_STAGE_BYTES;
@@ -468,7 +469,7 @@ __global__ void __launch_bounds__(THREADS, 1) scores_tc_kernel(const __grid_cons
                 if (row < nrows) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (col0 + i < k) scores[row * k + col0 + i] = (double)__uint_as_float(r[i]);
+                        if (col0 + i < k) scores[row * k + col0 + i] = (double)__uint_as_float(r[i]) - bias[col0 + i];
                 }
             }
             tc_fence_before();
@@ -507,7 +508,7 @@ static CUtensorMap map2d(const __half *X, uint64_t rows, uint32_t cols, uint32_t
 }  // namespace sc
 
 void scores_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, const double *W, uint32_t kpad,
-                    uint32_t k, double *scores) {
+                    uint32_t k, const double *bias, double *scores) {
     using namespace sc;
     if (n == 0) return;
     SRB_REQUIRE(kpad == SN && k <= SN, SRB_ERR_UNSUPPORTED, "tensor-core scores support up to 64 components");
@@ -520,7 +521,7 @@ void scores_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n
     const uint32_t ntiles = (uint32_t)((n + SM - 1) / SM);
     const unsigned grid = std::min<uint32_t>(ntiles, (uint32_t)ctx->sm_count);
     SRB_CUDA(cudaFuncSetAttribute(scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S_SMEM_BYTES));
-    SRB_LAUNCH(scores_tc_kernel, grid, THREADS, S_SMEM_BYTES, s, mzh, mzl, mwh, mwl, n, dpad / SBK, k, scores);
+    SRB_LAUNCH(scores_tc_kernel, grid, THREADS, S_SMEM_BYTES, s, mzh, mzl, mwh, mwl, n, dpad / SBK, k, bias, scores);
 }
 
 }  // namespace srb

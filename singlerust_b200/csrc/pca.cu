@@ -13,13 +13,23 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
-#include "bulk.cuh"
 #include "common.cuh"
 
 namespace srb {
 
 static unsigned nb(uint64_t n, unsigned t = 256) { return (unsigned)std::max<uint64_t>(1, (n + t - 1) / t); }
+
+// SRB_PCA_SHIFT=center: every panel column is centred before the Gram product (round-1 behaviour); default "sparse": sparse
+// genes keep their zeros and are corrected by the rank-one term afterwards (see sel_stats_kernel)
+static int sparse_shift_mode() {
+    static const int v = [] {
+        const char *e = getenv("SRB_PCA_SHIFT");
+        return (e && !strcmp(e, "center")) ? 0 : 1;
+    }();
+    return v;
+}
 
 // lut[col] = position in the selection, -1 if not selected; duplicates: the LAST position wins (HashMap insert
 // order, shared/mod.rs:241)
@@ -79,9 +89,10 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
 // 16-byte stores; step 2 overwrites the stored entries with 2-byte scattered stores — they hit the lines step 1 just
 // put into L2, so DRAM sees each line once. __syncwarp() orders the two steps inside the warp.
 // HBM: 8 B/nnz in, 4*dpad B/row out.
-// (A first cp.async.bulk-staged variant in which 8 warps worked on one tile together — a barrier per tile, the row of an
-// entry found by binary search — took 12.5 ms against 4.5 ms for this kernel and was removed; the row-owning form that
-// replaced it is densify_panels_bulk_kernel below.)
+// (Two cp.async.bulk-staged variants were measured in round 2 and removed: 8 warps sharing one tile, the row of an entry found
+// by binary search, a barrier per tile: 12.5 ms; row-owning consumer warps reading a shared-memory ring like K1, selection
+// bitmap in shared memory: 4.95 ms. This kernel with 8 loads per array in flight per lane: 4.3-4.4 ms. Staging the loads does
+// not help here because the stall is the dependent chain LUT -> (shift, 1/sd) -> store of the selected 7 %, not the stream.)
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const uint16_t *__restrict__ lut,
@@ -197,109 +208,6 @@ __global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_
     }
 }
 
-// K6, bulk-staged form (f32 values, <= 32 768 genes, rows of >= 128 entries on average) — the structure that took K1 from
-// 0.69 to 0.88 of the HBM peak: the (index, value) run of a CTA's rows is streamed tile by tile (1024 entries: 4 KB + 4 KB)
-// into a 4-stage shared-memory ring by cp.async.bulk (one producer thread), and 4 consumer warps own whole rows: a warp
-// writes its row's implicit-zero constants (16-byte stores), then walks the row out of shared memory, lane-strided. The
-// selection test is a 4 KB bitmap in shared memory (93 % of the entries end there); only selected entries go on to the
-// LUT / (shift, 1 / sd) lookups and the two 2-byte stores, which hit the lines the fill just put into L2. Every consumer warp
-// waits for and releases every tile exactly once, in order (rows span tiles).
-namespace k6b {
-constexpr int TILE = 1024, STAGES = 4, MAX_GENES = 32768;
-}
-__global__ void sel_bitmap_kernel(const uint32_t *__restrict__ sel, uint64_t n_sel, uint32_t *__restrict__ bits) {
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_sel) atomicOr(&bits[sel[j] >> 5], 1u << (sel[j] & 31));
-}
-template <int CONSUMERS>
-__global__ void __launch_bounds__(32 * (1 + CONSUMERS)) densify_panels_bulk_kernel(
-    const int64_t *__restrict__ off, const uint32_t *__restrict__ idx, const float *__restrict__ val, const uint16_t *__restrict__ lut,
-    const uint32_t *__restrict__ selbits, const float2 *__restrict__ shis, const __half *__restrict__ zc_h, const __half *__restrict__ zc_l,
-    uint64_t nrows, uint32_t rows_per_cta, uint32_t dpad, __half *__restrict__ Xh, __half *__restrict__ Xl) {
-    using namespace k6b;
-    __shared__ __align__(128) uint32_t s_idx[STAGES][TILE];
-    __shared__ __align__(128) float s_val[STAGES][TILE];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES];
-    __shared__ uint32_t s_bits[MAX_GENES / 32];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
-    if (r0 >= nrows) return;
-    const uint64_t r1 = min(r0 + (uint64_t)rows_per_cta, nrows);
-    for (uint32_t i = threadIdx.x; i < MAX_GENES / 32; i += blockDim.x) s_bits[i] = selbits[i];
-    const int64_t a0 = off[r0], b1 = off[r1];
-    const int64_t base = a0 & ~(int64_t)3;
-    const uint32_t ntiles = (uint32_t)((b1 - base + TILE - 1) / TILE);
-    const uint32_t full0 = bulk::smem_u32(&bars[0]), empty0 = bulk::smem_u32(&bars[STAGES]);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) bulk::mbar_init(full0 + 8 * s, 1), bulk::mbar_init(empty0 + 8 * s, CONSUMERS);
-        bulk::mbar_init_fence();
-    }
-    __syncthreads();
-    if (warp == 0) {
-        if (lane == 0) {
-            for (uint32_t t = 0; t < ntiles; ++t) {
-                const uint32_t s = t % STAGES;
-                bulk::mbar_wait(empty0 + 8 * s, ((t / STAGES) & 1) ^ 1);
-                const int64_t lo = base + (int64_t)t * TILE;
-                const uint32_t n = (uint32_t)min((int64_t)TILE, (b1 - lo + 3) & ~(int64_t)3);
-                bulk::mbar_arrive_expect_tx(full0 + 8 * s, 8 * n);
-                bulk::copy_g2s(bulk::smem_u32(&s_idx[s][0]), idx + lo, 4 * n, full0 + 8 * s);
-                bulk::copy_g2s(bulk::smem_u32(&s_val[s][0]), val + lo, 4 * n, full0 + 8 * s);
-            }
-        }
-        return;
-    }
-    const uint32_t cw = warp - 1;
-    const uint32_t nvec = dpad / 8;
-    const uint4 *ch = reinterpret_cast<const uint4 *>(zc_h), *cl = reinterpret_cast<const uint4 *>(zc_l);
-    uint32_t t_cur = 0;
-    bool have = false;
-    auto release_until = [&](uint32_t t) {
-        while (t_cur < t) {
-            if (!have) bulk::mbar_wait(full0 + 8 * (t_cur % STAGES), (t_cur / STAGES) & 1);
-            __syncwarp();
-            if (lane == 0) bulk::mbar_arrive(empty0 + 8 * (t_cur % STAGES));
-            ++t_cur, have = false;
-        }
-    };
-    for (uint64_t r = r0 + cw; r < r1; r += CONSUMERS) {
-        const int64_t a = off[r], b = off[r + 1];
-        __half *rh = Xh + r * dpad, *rl = Xl + r * dpad;
-        {
-            uint4 *oh = reinterpret_cast<uint4 *>(rh), *ol = reinterpret_cast<uint4 *>(rl);
-            for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
-        }
-        __syncwarp();
-        int64_t pos = a;
-        while (pos < b) {
-            const uint32_t t = (uint32_t)((pos - base) / TILE);
-            release_until(t);
-            if (!have) bulk::mbar_wait(full0 + 8 * (t % STAGES), (t / STAGES) & 1), have = true;
-            const int64_t tile_lo = base + (int64_t)t * TILE;
-            const int e = (int)(min(b, tile_lo + TILE) - tile_lo);
-            const uint32_t *ti = s_idx[t % STAGES];
-            const float *tv = s_val[t % STAGES];
-            auto one = [&](int i) {
-                const uint32_t c = ti[i];
-                if ((s_bits[c >> 5] >> (c & 31)) & 1u) {
-                    const uint32_t p = lut[c];
-                    const float2 si = shis[p];
-                    const float z = (tv[i] - si.x) * si.y;
-                    const __half h = __float2half_rn(z);
-                    rh[p] = h;
-                    rl[p] = __float2half_rn(z - __half2float(h));
-                }
-            };
-            int i = (int)(pos - tile_lo) + (int)lane;
-            for (; i + 96 < e; i += 128) one(i), one(i + 32), one(i + 64), one(i + 96);
-            for (; i < e; i += 32) one(i);
-            pos = tile_lo + e;
-        }
-        __syncwarp();
-    }
-    release_until(ntiles);
-}
-
 // K7 (validation path): G += X^T X in fp64 on CUDA cores. 64x64 output tile per CTA, upper-triangular tiles only,
 // split over row ranges (fp64 REDs into G). x = (double)xh + (double)xl.
 static constexpr int GT = 64, GK = 16;
@@ -386,17 +294,24 @@ static void allreduce_gram(srb_ctx *c, double *G, uint32_t dpad, uint64_t n_sel)
     SRB_LAUNCH(tri_unpack_kernel, nb((uint64_t)d * d), 256, 0, s, T->as<double>(), dpad, d, G);
 }
 
-// per selected gene: mean over ALL cells and 1/std (ddof 0) from the global per-gene moments; shift = mean when
-// centring; zc = split-fp16 of the standardised value of an implicit zero
+// per selected gene: mean over ALL cells and 1/std (ddof 0) from the global per-gene moments.
+// Panel column j holds z' = (x - s_j) / sd_j. For a SPARSE gene (mean^2 <= 0.25 var: most cells do not express it) the panel
+// shift s_j is 0 instead of the mean, so the implicit zeros of the count matrix stay exact zeros in the fp16 panels (95 % of
+// the entries at the bench density) and the products that reach the tensor cores are mostly zero: fewer terms per fp32
+// accumulation chunk (less rounding) and far less switching in the MMA datapath, which runs at the 1 kW power cap. The
+// column is then off by the constant w_j = (mean_j - s_j) / sd_j:  Z = Z' - 1 w^T,  Z^T Z = Z'^T Z' - n w w^T  (Z'^T 1 = n w),
+// scores = Z' V - 1 (w^T V): both corrections are exact fp64 rank-one terms (corr_kernel, components_kernel -> bias). The
+// cancellation is benign exactly when w is small, which is the criterion; dense genes keep the centre-first form (w_j = 0),
+// whose reason is given at the top of the file.
 __global__ void sel_stats_kernel(const uint32_t *__restrict__ sel, uint64_t n_sel, uint32_t dpad, const double *__restrict__ sum,
-                                 const double *__restrict__ sq, double n_cells, int center, int scale,
-                                 double *__restrict__ shift, double *__restrict__ inv_sd, float *__restrict__ shf,
+                                 const double *__restrict__ sq, double n_cells, int center, int scale, int sparse_shift,
+                                 double *__restrict__ shift, double *__restrict__ inv_sd, double *__restrict__ wres, float *__restrict__ shf,
                                  float *__restrict__ isf, __half *__restrict__ zc_h, __half *__restrict__ zc_l,
                                  uint32_t *__restrict__ flag) {
     const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= dpad) return;
     if (j >= n_sel) {
-        shift[j] = 0.0, inv_sd[j] = 0.0, shf[j] = 0.f, isf[j] = 0.f;
+        shift[j] = 0.0, inv_sd[j] = 0.0, wres[j] = 0.0, shf[j] = 0.f, isf[j] = 0.f;
         zc_h[j] = __float2half(0.f), zc_l[j] = __float2half(0.f);
         return;
     }
@@ -410,8 +325,10 @@ __global__ void sel_stats_kernel(const uint32_t *__restrict__ sel, uint64_t n_se
         if (sd > 0.0) is = 1.0 / sd;
         else { is = 0.0; atomicOr(flag, 1u); }  // the reference divides by zero here (NaN columns)
     }
-    const double sh = center ? mean : 0.0;  // pca/mod.rs:98-104: subtract only when centring
-    shift[j] = sh, inv_sd[j] = is, shf[j] = (float)sh, isf[j] = (float)is;
+    const double sh_full = center ? mean : 0.0;  // pca/mod.rs:98-104: subtract only when centring
+    const bool sparse = sparse_shift && center && mean * mean <= 0.25 * var;
+    const double sh = sparse ? 0.0 : sh_full;    // what the panels subtract
+    shift[j] = sh_full, inv_sd[j] = is, wres[j] = (sh_full - sh) * is, shf[j] = (float)sh, isf[j] = (float)is;
     const double z0 = (0.0 - sh) * is;
     const __half h = __double2half(z0);
     zc_h[j] = h;
@@ -422,11 +339,11 @@ __global__ void sel_stats_kernel(const uint32_t *__restrict__ sel, uint64_t n_se
 // scaling): the diagonal sums only positive terms, which is where fp32 chunk accumulation has a systematic bias.
 __global__ void corr_kernel(const double *__restrict__ G, uint32_t dpad, uint64_t n_sel, const uint32_t *__restrict__ sel,
                             const double *__restrict__ sum, const double *__restrict__ sq, const double *__restrict__ shift,
-                            const double *__restrict__ inv_sd, double n_cells, double *__restrict__ C) {
+                            const double *__restrict__ inv_sd, const double *__restrict__ wres, double n_cells, double *__restrict__ C) {
     const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_sel * n_sel) return;
     const uint64_t i = e / n_sel, j = e % n_sel;
-    double v = G[i * dpad + j];
+    double v = G[i * dpad + j] - n_cells * wres[i] * wres[j];  // Z^T Z = Z'^T Z' - n w w^T (sparse panel shift)
     if (i == j) {
         const uint32_t g = sel[i];
         const double sh = shift[i], is = inv_sd[i];
@@ -451,8 +368,8 @@ __global__ void trace_kernel(const double *__restrict__ C, uint64_t n_sel, doubl
 // Sign convention: the entry of largest magnitude of every component is positive (deterministic across runs).
 // comps[j][c] (row-major n_sel x k), W[p][c] = comps[p][c] (row-major dpad x kpad, zero padded), evr[c] = lambda_c / trace
 __global__ void components_kernel(const double *__restrict__ evec, const double *__restrict__ evals_asc, uint32_t npairs, uint64_t n_sel,
-                                  uint32_t k, uint32_t kpad, const double *__restrict__ trace, double *__restrict__ comps,
-                                  double *__restrict__ W, double *__restrict__ evr) {
+                                  uint32_t k, uint32_t kpad, const double *__restrict__ trace, const double *__restrict__ wres,
+                                  double *__restrict__ comps, double *__restrict__ W, double *__restrict__ evr, double *__restrict__ bias) {
     const uint32_t c = blockIdx.x;
     if (c >= k) return;
     const double *v = evec + (uint64_t)(npairs - 1 - c) * n_sel;
@@ -476,19 +393,28 @@ __global__ void components_kernel(const double *__restrict__ evec, const double 
     }
     const double sgn = v[s_idx[0]] < 0.0 ? -1.0 : 1.0;
     __syncthreads();
+    double b = 0.0;  // bias[c] = sum_j w_j V[j][c]: the constant the scores of the shifted panels are off by
     for (uint64_t j = threadIdx.x; j < n_sel; j += blockDim.x) {
         const double x = sgn * v[j];
         comps[j * k + c] = x;
         W[j * kpad + c] = x;
+        b += wres[j] * x;
     }
-    if (threadIdx.x == 0) evr[c] = evals_asc[npairs - 1 - c] / trace[0];
+    s_val[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_val[threadIdx.x] += s_val[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) evr[c] = evals_asc[npairs - 1 - c] / trace[0], bias[c] = s_val[0];
 }
 
 // K9 (validation path): scores[r][c] = sum_p z[r][p] W[p][c] in fp64 on CUDA cores. One warp per 4 rows; lane l owns
 // components c0+l and c0+l+32; W rows are read once per 4 rows (L1), z values are warp-broadcast.
 __global__ void __launch_bounds__(256) scores_simt_kernel(const __half *__restrict__ Xh, const __half *__restrict__ Xl,
                                                           uint64_t nrows, uint32_t dpad, const double *__restrict__ W,
-                                                          uint32_t kpad, uint32_t k, uint32_t c0, double *__restrict__ scores) {
+                                                          uint32_t kpad, uint32_t k, uint32_t c0, const double *__restrict__ bias,
+                                                          double *__restrict__ scores) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
     const uint64_t nwarps = (uint64_t)gridDim.x * 8;
@@ -517,8 +443,8 @@ __global__ void __launch_bounds__(256) scores_simt_kernel(const __half *__restri
         for (int i = 0; i < 4; ++i) {
             const uint64_t r = r0 + i;
             if (r < nrows) {
-                if (c0 + lane < k) scores[r * k + c0 + lane] = acc[i][0];
-                if (c0 + lane + 32 < k) scores[r * k + c0 + lane + 32] = acc[i][1];
+                if (c0 + lane < k) scores[r * k + c0 + lane] = acc[i][0] - bias[c0 + lane];
+                if (c0 + lane + 32 < k) scores[r * k + c0 + lane + 32] = acc[i][1] - bias[c0 + lane + 32];
             }
         }
     }
@@ -544,10 +470,10 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
 
     Buf flag = dev_zeros(s, 4);
     Buf shift = dev_alloc(s, 8 * dpad), inv_sd = dev_alloc(s, 8 * dpad), zc_h = dev_alloc(s, 2 * dpad), zc_l = dev_alloc(s, 2 * dpad);
-    Buf shf = dev_alloc(s, 4 * dpad), isf = dev_alloc(s, 4 * dpad);
+    Buf shf = dev_alloc(s, 4 * dpad), isf = dev_alloc(s, 4 * dpad), wres = dev_alloc(s, 8 * dpad);
     SRB_LAUNCH(sel_stats_kernel, nb(dpad), 256, 0, s, d_sel, n_sel, dpad, m->minor.sum->as<double>(), m->minor.sq->as<double>(),
-               n_cells, center ? 1 : 0, scale ? 1 : 0, shift->as<double>(), inv_sd->as<double>(), shf->as<float>(), isf->as<float>(),
-               zc_h->as<__half>(), zc_l->as<__half>(), flag->as<uint32_t>());
+               n_cells, center ? 1 : 0, scale ? 1 : 0, sparse_shift_mode(), shift->as<double>(), inv_sd->as<double>(), wres->as<double>(),
+               shf->as<float>(), isf->as<float>(), zc_h->as<__half>(), zc_l->as<__half>(), flag->as<uint32_t>());
 
     SRB_TRACE("lut + sel_stats");
     SRB_REQUIRE(n_sel < 65535, SRB_ERR_UNSUPPORTED, "at most 65534 selected features");
@@ -565,22 +491,9 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             const char *e = getenv("SRB_DENSIFY_PIPE");
             pipe = (e && e[0] == '0') ? 0 : 1;  // default: register double-buffered variant (4.40 vs 4.68 ms at L)
         }
-        static const int bulk_on = [] {
-            const char *e = getenv("SRB_K6_BULK");
-            return (e && e[0] == '0') ? 0 : 1;
-        }();
-        if (m->vdtype == SRB_F32 && bulk_on && M <= (uint64_t)k6b::MAX_GENES && (double)m->st->nnz / (double)n >= 128.0) {
-            Buf bits = dev_zeros(s, 4 * (k6b::MAX_GENES / 32));
-            SRB_LAUNCH(sel_bitmap_kernel, nb(n_sel), 256, 0, s, d_sel, n_sel, bits->as<uint32_t>());
-            uint64_t rpc = (n + (uint64_t)c->sm_count * 24 - 1) / ((uint64_t)c->sm_count * 24);
-            rpc = std::max<uint64_t>(16, std::min<uint64_t>(rpc, 256));
-            SRB_LAUNCH(densify_panels_bulk_kernel<4>, (unsigned)((n + rpc - 1) / rpc), 160, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(),
-                       m->values->as<float>(), lut16->as<uint16_t>(), bits->as<uint32_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n,
-                       (uint32_t)rpc, dpad, Xh->as<__half>(), Xl->as<__half>());
-        } else {
         static const int batch8 = [] {
             const char *e = getenv("SRB_DENSIFY_BATCH");
-            return (e && atoi(e) == 8) ? 1 : 0;
+            return (e && atoi(e) == 4) ? 0 : 1;  // 8 loads per array in flight per lane: 4.30-4.38 ms against 4.64 for 4 (measured)
         }();
         if (m->vdtype == SRB_F32 && pipe && batch8) {
             SRB_LAUNCH((densify_panels_pipe_kernel<float, 8>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
@@ -590,7 +503,6 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
             SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
-        }
         }
     }
     SRB_TRACE("panels alloc + densify enqueue");
@@ -617,13 +529,13 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     }
     // K8: correlation matrix + symmetric eigendecomposition
     Buf C = dev_alloc(s, 8 * n_sel * n_sel), evals = dev_alloc(s, 8 * n_sel), tr = dev_alloc(s, 8);
-    Buf comps = dev_alloc(s, 8 * n_sel * k), W = dev_zeros(s, 8 * (size_t)dpad * kpad), evr = dev_alloc(s, 8 * k);
+    Buf comps = dev_alloc(s, 8 * n_sel * k), W = dev_zeros(s, 8 * (size_t)dpad * kpad), evr = dev_alloc(s, 8 * k), bias = dev_zeros(s, 8 * kpad);
     {
         StageTimer t(c, ST_EIG);
-        SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, G->as<double>(), dpad, n_sel, d_sel, m->minor.sum->as<double>(), m->minor.sq->as<double>(), shift->as<double>(), inv_sd->as<double>(), n_cells, C->as<double>());
+        SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, G->as<double>(), dpad, n_sel, d_sel, m->minor.sum->as<double>(), m->minor.sq->as<double>(), shift->as<double>(), inv_sd->as<double>(), wres->as<double>(), n_cells, C->as<double>());
         SRB_LAUNCH(trace_kernel, 1, 256, 0, s, C->as<double>(), n_sel, tr->as<double>());
         const uint32_t npairs = sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, (uint32_t)k, evals->as<double>());
-        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), npairs, n_sel, (uint32_t)k, kpad, tr->as<double>(), comps->as<double>(), W->as<double>(), evr->as<double>());
+        SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), npairs, n_sel, (uint32_t)k, kpad, tr->as<double>(), wres->as<double>(), comps->as<double>(), W->as<double>(), evr->as<double>(), bias->as<double>());
     }
     SRB_TRACE("eig");
     // K9 scores
@@ -631,11 +543,11 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     if (n) {
         StageTimer t(c, ST_SCORES);
         if (gram_mode == 0 && k <= 64) {
-            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, (uint32_t)k, scores->as<double>());
+            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, (uint32_t)k, bias->as<double>(), scores->as<double>());
         } else {
             const unsigned grid = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)c->sm_count * 16);
             for (uint32_t c0 = 0; c0 < k; c0 += 64)
-                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, (uint32_t)k, c0, scores->as<double>());
+                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, dpad, W->as<double>(), kpad, (uint32_t)k, c0, bias->as<double>(), scores->as<double>());
         }
     }
     if (out.scores && n) SRB_CUDA(cudaMemcpyAsync(out.scores, scores->p, 8 * n * k, cudaMemcpyDeviceToHost, s));
@@ -668,7 +580,7 @@ struct srb_pca_stream {
     bool center = true, scale = true, fitted = false;
     int gram_mode = 0;
     uint32_t dpad = 0, kpad = 0;
-    srb::Buf sel, sum, sq, lut16, shis, zc_h, zc_l, shift, inv_sd, flag, G, W, comps, evr;
+    srb::Buf sel, sum, sq, lut16, shis, zc_h, zc_l, shift, inv_sd, wres, bias, flag, G, W, comps, evr;
 };
 
 namespace srb {
@@ -740,9 +652,10 @@ int32_t srb_pca_stream_begin(srb_ctx *ctx, uint64_t ncols, uint64_t ncells_total
     ps->flag = dev_zeros(s, 4);
     ps->shift = dev_alloc(s, 8 * dpad), ps->inv_sd = dev_alloc(s, 8 * dpad), ps->zc_h = dev_alloc(s, 2 * dpad), ps->zc_l = dev_alloc(s, 2 * dpad);
     Buf shf = dev_alloc(s, 4 * dpad), isf = dev_alloc(s, 4 * dpad);
+    ps->wres = dev_alloc(s, 8 * dpad);
     SRB_LAUNCH(sel_stats_kernel, nb(dpad), 256, 0, s, ps->sel->as<uint32_t>(), n_sel, dpad, ps->sum->as<double>(), ps->sq->as<double>(),
-               ps->n_cells, ps->center ? 1 : 0, ps->scale ? 1 : 0, ps->shift->as<double>(), ps->inv_sd->as<double>(), shf->as<float>(),
-               isf->as<float>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), ps->flag->as<uint32_t>());
+               ps->n_cells, ps->center ? 1 : 0, ps->scale ? 1 : 0, sparse_shift_mode(), ps->shift->as<double>(), ps->inv_sd->as<double>(),
+               ps->wres->as<double>(), shf->as<float>(), isf->as<float>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), ps->flag->as<uint32_t>());
     ps->lut16 = dev_alloc(s, 2 * (M + 1)), ps->shis = dev_alloc(s, 8 * dpad);
     SRB_LAUNCH(lut16_kernel, nb(M), 256, 0, s, lut->as<int>(), ps->lut16->as<uint16_t>(), M);
     SRB_LAUNCH(shis_kernel, nb(dpad), 256, 0, s, shf->as<float>(), isf->as<float>(), ps->shis->as<float2>(), dpad);
@@ -812,12 +725,13 @@ int32_t srb_pca_stream_fit(srb_pca_stream *ps, double *components, double *expla
     if (c->nranks > 1) allreduce_gram(c, ps->G->as<double>(), dpad, n_sel);  // ranks hold disjoint chunks
     Buf C = dev_alloc(s, 8 * n_sel * n_sel), evals = dev_alloc(s, 8 * n_sel), tr = dev_alloc(s, 8);
     ps->comps = dev_alloc(s, 8 * n_sel * k), ps->W = dev_zeros(s, 8 * (size_t)dpad * kpad), ps->evr = dev_alloc(s, 8 * k);
+    ps->bias = dev_zeros(s, 8 * kpad);
     SRB_LAUNCH(corr_kernel, nb(n_sel * n_sel), 256, 0, s, ps->G->as<double>(), dpad, n_sel, ps->sel->as<uint32_t>(), ps->sum->as<double>(),
-               ps->sq->as<double>(), ps->shift->as<double>(), ps->inv_sd->as<double>(), ps->n_cells, C->as<double>());
+               ps->sq->as<double>(), ps->shift->as<double>(), ps->inv_sd->as<double>(), ps->wres->as<double>(), ps->n_cells, C->as<double>());
     SRB_LAUNCH(trace_kernel, 1, 256, 0, s, C->as<double>(), n_sel, tr->as<double>());
     const uint32_t npairs = sym_eig_desc(c, C->as<double>(), (uint32_t)n_sel, (uint32_t)k, evals->as<double>());
     SRB_LAUNCH(components_kernel, (unsigned)k, 256, 0, s, C->as<double>(), evals->as<double>(), npairs, n_sel, (uint32_t)k, kpad, tr->as<double>(),
-               ps->comps->as<double>(), ps->W->as<double>(), ps->evr->as<double>());
+               ps->wres->as<double>(), ps->comps->as<double>(), ps->W->as<double>(), ps->evr->as<double>(), ps->bias->as<double>());
     if (components) SRB_CUDA(cudaMemcpyAsync(components, ps->comps->p, 8 * n_sel * k, cudaMemcpyDeviceToHost, s));
     if (explained_variance_ratio) SRB_CUDA(cudaMemcpyAsync(explained_variance_ratio, ps->evr->p, 8 * k, cudaMemcpyDeviceToHost, s));
     uint32_t hflag = 0;
@@ -844,11 +758,11 @@ int32_t srb_pca_stream_transform(srb_pca_stream *ps, srb_mat *chunk, double *sco
         stream_densify(ps, chunk, Xh, Xl);
         Buf out = dev_alloc(s, 8 * n * k);
         if (ps->gram_mode == 0 && k <= 64 && n >= 256) {
-            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, out->as<double>());
+            scores_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, ps->bias->as<double>(), out->as<double>());
         } else {
             const unsigned grid = (unsigned)std::min<uint64_t>((n + 31) / 32, (uint64_t)c->sm_count * 16);
             for (uint32_t c0 = 0; c0 < k; c0 += 64)
-                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, c0, out->as<double>());
+                SRB_LAUNCH(scores_simt_kernel, grid, 256, 0, s, Xh->as<__half>(), Xl->as<__half>(), n, ps->dpad, ps->W->as<double>(), ps->kpad, (uint32_t)k, c0, ps->bias->as<double>(), out->as<double>());
         }
         SRB_CUDA(cudaMemcpyAsync(scores, out->p, 8 * n * k, cudaMemcpyDeviceToHost, s));
         SRB_CUDA(cudaStreamSynchronize(s));
