@@ -16,6 +16,8 @@ The same line also carries, measured in the same run (each with its own CUDA-eve
   xxl       configs[4]: the backed chunk stream (131 072-row chunks from pinned host memory, 1.25M cells per GPU = 10M on 8)
             through the full pipeline: chunks uploaded once and kept resident, and the one-chunk-resident three-pass form
   faithful  the headline step in SRB_VALUES_FAITHFUL mode (f64 values and accumulation, the reference's arithmetic)
+  pipelined the headline workload with two batches in flight on the GPU (N = 1): throughput when the eigensolver of one
+            batch overlaps the streaming kernels of the next
 `--scaling strong` / `--config xl|xxl` make one of them the main line instead.
 """
 from __future__ import annotations
@@ -66,7 +68,7 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --cells per GPU; strong: --cells in total")
     ap.add_argument("--config", default="l", choices=["l", "xl", "xxl"], help="BASELINE.json configs[2] (default) / [3] / [4] as the main line")
     ap.add_argument("--no-legs", action="store_true", help="skip the strong / xl / xxl / faithful legs")
-    ap.add_argument("--legs", default="strong,xl,xxl,faithful", help="comma list of legs to run after the main line")
+    ap.add_argument("--legs", default="strong,xl,xxl,faithful,pipelined", help="comma list of legs to run after the main line")
     ap.add_argument("--xxl-cells-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--xxl-chunk", type=int, default=131_072)
     return ap.parse_args()
@@ -549,6 +551,8 @@ def run_ours(args):
         guarded("faithful", lambda: leg_faithful(env, args, n, cells_total))
         if isinstance(line.get("faithful"), dict) and "value" in line["faithful"]:
             line["value_faithful"], line["ms_per_step_faithful"] = line["faithful"]["value"], line["faithful"]["ms_per_step"]
+    if "pipelined" in legs and L == 1 and world == 1:
+        guarded("pipelined", lambda: leg_pipelined(env, args, n, cells_total))
     if "strong" in legs:
         if world == 1:
             line["strong"] = {"cells_total": args.cells, "n_gpus": 1, "value": value, "ms_per_step": ms_step,
@@ -603,6 +607,20 @@ def leg_faithful(env, args, n, cells_total):
     c.close()
     return {"value": cells_total / (r["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_per_step"], "stage_ms": r["stage_ms"],
             "dtype": "f64 values / f64 accumulate (SRB_VALUES_FAITHFUL; Gram still on tcgen05 from split-fp16 panels)"}
+
+
+def leg_pipelined(env, args, n, cells_total):
+    """Throughput with two batches in flight on the GPU (two contexts, streams and host threads): the latency-bound
+    eigensolver of one batch overlaps the bandwidth-bound kernels of the other. Same work per batch, nothing skipped; the
+    main line stays single-lane so that its per-stage times are uncontended."""
+    cs = [env.new_ctx() for _ in range(2)]
+    mats, _, _ = make_shards(env, args, cs, SEED, cells_total=cells_total)
+    r = timed_pipeline(env, args, cs, mats, max(4, min(args.steps, 10)) // 2 * 2, 4, settle=False)
+    for mt in mats:
+        mt.free()
+    for c in cs:
+        c.close()
+    return {"value": cells_total / (r["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_per_step"], "batches_in_flight": 2}
 
 
 def leg_sharded(env, args, ctx, seed, cells_total, what):
