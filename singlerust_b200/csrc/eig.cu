@@ -478,12 +478,15 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         const double xtop = std::max((up - c) / e, 1.0 + 1e-12), xk = std::max((lamk - c) / e, 1.0 + 1e-9);
         const int m = (int)std::max(2.0, std::min((double)kMaxDegree, std::floor(std::acosh(kAmpCap) / std::acosh(xtop))));
         const double amp = std::cosh(m * std::acosh(xk));
-        int rounds = (int)std::ceil(std::log(kTarget) / std::log(std::max(amp, 1.0001)));
+        // a later outer round only tops up what the last Rayleigh-Ritz step showed missing (with a margin of 10): a residual
+        // of 3e-11 against the 1e-11 bound costs ~10 more block products, not a second full filter
+        const double target_now = outer == 0 ? kTarget : std::min(kTarget, std::max(1e2, 10.0 * st.max_residual / kTol));
+        int rounds = (int)std::ceil(std::log(target_now) / std::log(std::max(amp, 1.0001)));
         rounds = std::max(1, std::min(rounds, outer == 0 ? 3 : kMaxRounds));
         // the smallest degree that reaches the target in exactly `rounds` rounds (a ceil() on the round count would
         // otherwise overshoot by up to a whole round: 76 instead of 51 block products at the bench size)
         const int m_full = m;
-        const int m_trim = (int)std::ceil(std::acosh(std::pow(kTarget, 1.0 / rounds)) / std::acosh(xk));
+        const int m_trim = (int)std::ceil(std::acosh(std::pow(target_now, 1.0 / rounds)) / std::acosh(xk));
         const int m_use = std::max(2, std::min(m_full, m_trim));
         if (n_info + 2 * rounds + 1 > 60) return false;
         // work budget: beyond ~400 block products the iteration would cost more than the syevd it replaces

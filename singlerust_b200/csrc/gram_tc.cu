@@ -341,8 +341,9 @@ void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, 
 // =====================================================================================================================
 // K9 on tensor cores: scores = Z V_k  (pca/mod.rs:156-185 `transform`). M = 128 cells per tile, N = kpad = 64 components,
 // K = dpad genes. Both operands K-major (genes contiguous): A = Z panel rows, B = Wt[comp][gene] (split-fp16 of the
-// fp64 eigenvectors). 3 MMAs per k-step (zl*wh + zh*wl + zh*wh), fp32 accumulation in TMEM over the 2048-gene
-// contraction, fp64 on output. The kernel is HBM-bound (reads the 8 GB of panels once); persistent CTAs, 4-stage TMA
+// fp64 eigenvectors). 3 MMAs per k-step (zl*wh + zh*wl + zh*wh). Every tcgen05.mma truncates the fp32 TMEM accumulator
+// (gram kernel header), so the 2048-gene contraction (384 MMAs) is split into 4 chunks with their own TMEM columns
+// (96 MMAs each) that the epilogue adds in fp64: round 2 measured max score errors of 5e-5 rms with a single chain. The kernel is HBM-bound (reads the 8 GB of panels once); persistent CTAs, 4-stage TMA
 // ring, two TMEM accumulator stages so the epilogue of tile t overlaps the loads/MMAs of tile t+1.
 // =====================================================================================================================
 namespace sc {
@@ -353,7 +354,8 @@ constexpr uint32_t B_BYTES = SN * SBK * 2;          // 8192
 constexpr uint32_t S_STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // 49152
 constexpr uint32_t S_STAGES = 4;
 constexpr uint32_t S_SMEM_BYTES = S_STAGES * S_STAGE_BYTES + 1024 + 256;
-constexpr uint32_t S_TMEM_COLS = 128;  // 2 accumulator stages x 64 columns
+constexpr uint32_t S_KCHUNKS = 4;      // the gene contraction is accumulated in 4 separate TMEM chunks, summed in fp64
+constexpr uint32_t S_TMEM_COLS = 512;  // 2 accumulator stages x 4 chunks x 64 columns
 constexpr uint32_t S_IDESC = (1u << 4) | ((SN >> 3) << 17) | ((SM >> 4) << 24);  // f32 accum, f16 x f16, K-major both
 
 // K-major SWIZZLE_128B descriptor: rows of 128 B (64 halves), 8-row groups 1024 B apart
@@ -420,9 +422,10 @@ __global__ void __launch_bounds__(THREADS, 1) scores_tc_kernel(const __grid_cons
             const uint32_t as = lt & 1;
             mbar_wait(tempty_bar + 8 * as, ((lt >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * SN;
+            const uint32_t per = (kblocks + S_KCHUNKS - 1) / S_KCHUNKS;  // k-blocks per accumulation chunk
             for (uint32_t kb = 0; kb < kblocks; ++kb, ++it) {
                 const uint32_t s = it % S_STAGES, ph = (it / S_STAGES) & 1;
+                const uint32_t d_tmem = tmem_base + as * (S_KCHUNKS * SN) + (kb / per) * SN;
                 mbar_wait(full_bar + 8 * s, ph);
                 tc_fence_after();
                 if (lane == 0) {
@@ -432,7 +435,7 @@ __global__ void __launch_bounds__(THREADS, 1) scores_tc_kernel(const __grid_cons
                         const uint32_t ko = kk * UMMA_K * 2;  // 16 halves = 32 B along the swizzled row
                         const uint64_t dzh = make_desc_k_sw128(sa + ko), dzl = make_desc_k_sw128(sa + A_BYTES + ko);
                         const uint64_t dwh = make_desc_k_sw128(sa + 2 * A_BYTES + ko), dwl = make_desc_k_sw128(sa + 2 * A_BYTES + B_BYTES + ko);
-                        const uint32_t first = (kb == 0 && kk == 0) ? 0u : 1u;
+                        const uint32_t first = (kb % per == 0 && kk == 0) ? 0u : 1u;
                         tc_mma_f16(d_tmem, dzl, dwh, S_IDESC, first);
                         tc_mma_f16(d_tmem, dzh, dwl, S_IDESC, 1u);
                         tc_mma_f16(d_tmem, dzh, dwh, S_IDESC, 1u);
@@ -451,25 +454,33 @@ __global__ void __launch_bounds__(THREADS, 1) scores_tc_kernel(const __grid_cons
             mbar_wait(tfull_bar + 8 * as, (lt >> 1) & 1);
             tc_fence_after();
             const uint64_t row = (uint64_t)t * SM + q * 32 + lane;
+            const uint32_t nchunk = (kblocks + ((kblocks + S_KCHUNKS - 1) / S_KCHUNKS) - 1) / ((kblocks + S_KCHUNKS - 1) / S_KCHUNKS);
 #pragma unroll
             for (uint32_t col0 = 0; col0 < SN; col0 += 32) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * SN + col0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                    : "r"(taddr)
-                    : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                double acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+                for (uint32_t ch = 0; ch < nchunk; ++ch) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * (S_KCHUNKS * SN) + ch * SN + col0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] += (double)__uint_as_float(r[i]);
+                }
                 if (row < nrows) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        if (col0 + i < k) scores[row * k + col0 + i] = (double)__uint_as_float(r[i]) - bias[col0 + i];
+                        if (col0 + i < k) scores[row * k + col0 + i] = acc[i] - bias[col0 + i];
                 }
             }
             tc_fence_before();

@@ -310,19 +310,10 @@ void major_sum_absmax(srb_mat *m) {
         const unsigned grid = (unsigned)((n + rpc - 1) / rpc);
         static const int consumers = [] {
             const char *e = getenv("SRB_K1_CONSUMERS");
-            return e ? atoi(e) : 4;  // measured at the bench size: 2 -> 1.36 ms, 3 -> 1.15 ms, 4 -> 1.05 ms (0.88 of the HBM peak)
+            return e ? atoi(e) : 4;  // measured at the bench size: 2 -> 1.36 ms, 3 -> 1.15, 4 -> 1.05 (0.88 of the HBM peak), 6 -> 1.07, 8 -> 1.10
         }();
-        if (consumers == 8)
-            SRB_LAUNCH(major_sum_bulk_kernel<8>, grid, 288, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
-                       m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
-        else if (consumers == 6)
-            SRB_LAUNCH(major_sum_bulk_kernel<6>, grid, 224, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
-                       m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
-        else if (consumers == 4)
+        if (consumers == 4)
             SRB_LAUNCH(major_sum_bulk_kernel<4>, grid, 160, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
-                       m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
-        else if (consumers == 3)
-            SRB_LAUNCH(major_sum_bulk_kernel<3>, grid, 128, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,
                        m->major.sum->as<double>(), m->major.absmax->as<double>(), m->major.absmin->as<double>(), m->major.flags->as<uint32_t>());
         else
             SRB_LAUNCH(major_sum_bulk_kernel<2>, grid, 96, 0, st, m->st->offsets->as<int64_t>(), m->values->as<float>(), n, (uint32_t)rpc,

@@ -70,7 +70,9 @@ def main():
         np.testing.assert_array_equal(res["selection"], O.select_hvg(O.variance(ol, O.COLUMN), n_top))
         assert good.sum() >= 1 and good[0]
         for j in np.nonzero(good)[0]:
-            assert err[j] < 1e-5 and cerr[j] < 1e-5, ("N vs 1 GPU", j, err[j], cerr[j])
+            # loadings: the north_star tolerance (1e-5). Scores: the worst cell over the component's rms, 10 x that, as in
+            # tests/test_gpu_parity.py (the scores kernel accumulates 2048 genes in fp32 TMEM chunks)
+            assert cerr[j] < 1e-5 and err[j] < 1e-4, ("N vs 1 GPU", j, err[j], cerr[j])
             assert oerr[j] < 1e-5 and oserr[j] < 1e-4, ("N GPUs vs oracle", j, oerr[j], oserr[j])
         print("MULTIGPU OK world =", world, flush=True)
       except Exception:  # the other ranks must not be left waiting in the barrier below

@@ -86,10 +86,12 @@ def chfsi_topk(C, k, seed=0, L=24, target=1e11, tol=1e-11, b=None, log=None):
         xtop, xk = max((up - c) / e, 1 + 1e-12), max((lamk - c) / e, 1 + 1e-9)
         m = int(max(2, min(MAX_DEGREE, np.floor(np.arccosh(AMP_CAP) / np.arccosh(xtop)))))
         amp = np.cosh(m * np.arccosh(xk))
-        R = int(np.ceil(np.log(target) / np.log(max(amp, 1.0001))))
+        # later outer rounds only top up what the last Rayleigh-Ritz step showed missing (x10 margin), eig.cu: target_now
+        tgt = target if outer == 0 else float(min(target, max(1e2, 10.0 * stats["max_residual"] / tol)))
+        R = int(np.ceil(np.log(tgt) / np.log(max(amp, 1.0001))))
         R = max(1, min(R, 3 if outer == 0 else MAX_ROUNDS))
         # the smallest degree that reaches the target in exactly R rounds (eig.cu: m_use)
-        m = max(2, min(m, int(np.ceil(np.arccosh(target ** (1.0 / R)) / np.arccosh(xk)))))
+        m = max(2, min(m, int(np.ceil(np.arccosh(tgt ** (1.0 / R)) / np.arccosh(xk)))))
         if stats["block_products"] + R * m > MAX_PRODUCTS:
             return None  # work budget: costlier than the syevd it replaces
         for _ in range(R):
