@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--upload-mode", default="default", choices=["default", "device_narrow", "host_pack", "auto", "host_pack_values", "host_pack_adaptive", "host_pack_delta"],
                     help="how the e2e leg moves the u64 index array over PCIe (srb_ctx_set_upload_mode); default = library default")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory variant of the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-period-ms", type=int, default=100, help="nvidia-smi sampling period; 0 disables the sampler")
     ap.add_argument("--verbose", action="store_true")
@@ -879,6 +880,30 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
         ms_pipe = timed(max(args.e2e_steps, 5) * L, L)
         ms = min(ms_seq, ms_pipe)
     h2d, packed = ctx.last_upload()  # bytes that actually crossed PCIe (the library's own count)
+    chunks, idx_packed, val_packed = ctx.last_upload_chunks()
+    # the same step from PAGEABLE host memory (what a Rust Vec is): the library stages it through its pinned ring
+    pageable = None
+    if world == 1 and not args.no_pageable:
+        try:
+            hold = (off, idx, val)
+            off, idx, val = off.numpy().copy(), idx.numpy().copy(), val.numpy().copy()  # plain malloc'ed copies
+
+            def step_pageable(lane=0):
+                c = lanes[lane]
+                with link:
+                    m = _ffi.DeviceMatrix.upload(c, _ffi.CSR, n, args.genes, off.view(np.uint64), idx.view(np.uint64), val, nnz=nnz)
+                m.set_shard(rank * n, world * n)
+                m.pipeline_normalize_hvg_pca(TARGET_SUM, args.hvg, args.pcs, gram_mode=args.gram_mode, scores_out=lane_scores[lane])
+                m.free()
+
+            step = step_pageable
+            step(0)
+            ms_pg = timed(max(args.e2e_steps, 4) if L > 1 else args.e2e_steps, L)
+            pageable = {"ms_per_step": ms_pg, "value": world * n / (ms_pg * 1e-3), "steps_in_flight": L,
+                        "h2d_bytes_per_step": int(ctx.last_upload()[0])}
+            off, idx, val = hold
+        except Exception as ex:
+            pageable = {"error": str(ex)[:200]}
     for c in lanes[1:]:
         c.close()
     d2h = 8 * n * k + 8 * min(args.hvg, args.genes) * (k + 1) + 8 * k
@@ -887,6 +912,8 @@ def run_e2e(args, ctx, mat, rank, world, dev, barrier):
             "steps_in_flight": (L if (L > 1 and ms == ms_pipe) else 1), "ms_per_step_sequential": ms_seq,
             "ms_per_step_pipelined": (ms_pipe if L > 1 else None),
             "host_input_bytes_per_step": int(8 * (n + 1) + 12 * nnz), "upload_mode": "host_pack" if packed else "device_narrow",
+            "upload_chunks": {"chunks": chunks, "index_chunks_host_packed": idx_packed, "value_chunks_host_packed": val_packed},
+            "pageable_input": pageable,
             "host_layout": "u64 offsets + u64 indices + f32 values in pinned memory (the Rust usize layout)"}
 
 

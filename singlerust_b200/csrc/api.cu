@@ -21,7 +21,7 @@ void set_last_error(const std::string &msg) { t_last_error = msg; }
 // Every buffer of a context lives on that context's single stream, so a block released by ~DevBuf can be handed to
 // the next request in program order without any event bookkeeping. Steady-state steps therefore never reach the
 // driver allocator (measured: cudaMallocAsync pool growth stalls of 40-700 ms per step otherwise). Best fit within
-// 25 %; blocks beyond a 64 GB cache budget are returned to the driver.
+// 25 %; blocks beyond the cache budget (3/4 of the device) are returned to the driver.
 struct BlockCache {
     std::multimap<size_t, void *> free_blocks;
     size_t cached_bytes = 0;
@@ -44,7 +44,20 @@ bool ctx_alive(const srb_ctx *c) {
     std::lock_guard<std::mutex> lk(g_cache_mu);
     return g_live_ctx.count(c) != 0;
 }
-static constexpr size_t kCacheBudget = 64ull << 30;
+// free blocks kept per stream: three quarters of the device (135 GB on a B200). A request the driver cannot satisfy releases
+// the cache and retries (DevBuf::DevBuf), so a generous budget cannot cause an out-of-memory error; a tight one made the
+// 4M-cell step (57 GB of per-step buffers on top of a 48 GB matrix) go back to cudaMalloc / cudaFree every step (353 vs 83 ms)
+static size_t cache_budget() {
+    static const size_t v = [] {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || total_b == 0) {
+            (void)cudaGetLastError();
+            return (size_t)64 << 30;
+        }
+        return total_b / 4 * 3;
+    }();
+    return v;
+}
 
 static size_t round_block(size_t n) {
     if (n < 512) return 512;
@@ -69,7 +82,7 @@ DevBuf::DevBuf(size_t n, cudaStream_t s) : bytes(n), st(s) {
     cudaError_t e = cudaMalloc(&p, cap);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        release_cached_blocks(s);  // give everything back and retry once
+        release_all_cached_blocks();  // give every stream's free blocks back to the driver and retry once
         e = cudaMalloc(&p, cap);
     }
     if (e != cudaSuccess) {
@@ -88,7 +101,7 @@ DevBuf::~DevBuf() {
     BlockCache &c = g_caches[st];
     c.free_blocks.emplace(cap, p);
     c.cached_bytes += cap;
-    while (c.cached_bytes > kCacheBudget && !c.free_blocks.empty()) {
+    while (c.cached_bytes > cache_budget() && !c.free_blocks.empty()) {
         auto it = std::prev(c.free_blocks.end());
         cudaFree(it->second);
         c.cached_bytes -= it->first;
@@ -103,6 +116,15 @@ void release_cached_blocks(cudaStream_t s) {
     for (auto &kv : f->second.free_blocks) cudaFree(kv.second);
     f->second.free_blocks.clear();
     f->second.cached_bytes = 0;
+}
+void release_all_cached_blocks() {
+    std::vector<cudaStream_t> streams;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        for (auto &kv : g_caches)
+            if (g_live_streams.count(kv.first)) streams.push_back(kv.first);
+    }
+    for (cudaStream_t st : streams) release_cached_blocks(st);
 }
 Buf dev_alloc(cudaStream_t st, size_t bytes) { return std::make_shared<DevBuf>(bytes, st); }
 Buf dev_zeros(cudaStream_t st, size_t bytes) {

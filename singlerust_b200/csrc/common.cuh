@@ -73,6 +73,7 @@ void unregister_stream(cudaStream_t s);
 bool ctx_alive(const srb_ctx *c);
 // device buffer owned by one context stream; returned to that stream's block cache when the last reference drops
 void release_cached_blocks(cudaStream_t s);
+void release_all_cached_blocks();
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0, cap = 0;
