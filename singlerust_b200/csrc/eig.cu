@@ -348,11 +348,13 @@ struct PhaseTrace {
 static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, cudaStream_t es, double *d_C, uint32_t d, uint32_t k,
                        double *d_evals) {
     // tunables (round-2 sweeps without a rebuild; the defaults are the measured configuration):
-    //   SRB_CHFSI_KRYLOV  Krylov steps for the bounds (8..40, default 24)   SRB_CHFSI_BLOCK  block width b (multiple of 32)
+    //   SRB_CHFSI_KRYLOV  Krylov steps for the bounds (8..40, default 16: on the spectra of the 1M / 2M / 4M-cell bench
+    //                     matrices the resulting estimates give 58-70 block products every time, where 24 steps give 51
+    //                     on a lucky draw and 85-130, or a second outer round, on others)   SRB_CHFSI_BLOCK  block width b
     //   SRB_CHFSI_TARGET  log10 of the gain of the k-th eigenvalue over the cut per outer round (default 11)
     static const int L = [] {
         const char *e = getenv("SRB_CHFSI_KRYLOV");
-        return e ? std::max(8, std::min(40, atoi(e))) : 24;
+        return e ? std::max(8, std::min(40, atoi(e))) : 16;
     }();
     static const uint32_t b_env = [] {
         const char *e = getenv("SRB_CHFSI_BLOCK");
@@ -488,6 +490,7 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         const int m_full = m;
         const int m_trim = (int)std::ceil(std::acosh(std::pow(target_now, 1.0 / rounds)) / std::acosh(xk));
         const int m_use = std::max(2, std::min(m_full, m_trim));
+        const double amp_top_use = std::cosh(m_use * std::acosh(xtop));
         if (n_info + 2 * rounds + 1 > 60) return false;
         // work budget: beyond ~400 block products the iteration would cost more than the syevd it replaces
         if (st.block_products + rounds * m_use > kMaxProducts) return false;
@@ -508,8 +511,11 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
             st.block_products += m_use;
             if (Yc != Y) std::swap(Y, Yb);  // Y = filtered block, Yb = scratch
             trace.mark(1);
+            // CholeskyQR: one pass leaves an orthogonality error of ~eps * cond(Y)^2. Before Rayleigh-Ritz the block must be
+            // orthonormal to working precision (two passes); between filter rounds it only has to stay well conditioned,
+            // which one pass guarantees while the round amplified the top by <= 1e7 (error <= 1e-2)
             cholqr(Y);
-            cholqr(Y);
+            if (r + 1 == rounds || amp_top_use > 1e7) cholqr(Y);
             ++st.cholqr;
             trace.mark(2);
         }

@@ -1,7 +1,7 @@
 """NumPy twin of csrc/eig.cu: chfsi_topk — the same flow, constants and update rules, used to validate the algorithm on
 spectra a GPU box is not needed for (tests/test_chfsi_twin.py) and to explore tunables before spending GPU time.
 
-    bounds (L = 24 Krylov steps, CGS2) -> [filter degree m (amplification of the top capped at 1e8, trimmed to the
+    bounds (L = 16 Krylov steps, CGS2) -> [filter degree m (amplification of the top capped at 1e8, trimmed to the
     degree that reaches the target in R rounds) + CholeskyQR2] x R
     -> Rayleigh-Ritz -> residuals of the top k -> new cut / bounds -> ...            (at most 6 outer rounds)
 """
@@ -49,7 +49,7 @@ def block_width(d, k):
     return min(d // 4, ((max(3 * k, k + 96) + 31) // 32) * 32)
 
 
-def chfsi_topk(C, k, seed=0, L=24, target=1e11, tol=1e-11, b=None, log=None):
+def chfsi_topk(C, k, seed=0, L=16, target=1e11, tol=1e-11, b=None, log=None):
     """Returns (eigenvalues ascending, eigenvectors, stats) or None where the CUDA code would fall back to syevd."""
     rng = np.random.default_rng(seed)
     d = C.shape[0]
@@ -94,11 +94,12 @@ def chfsi_topk(C, k, seed=0, L=24, target=1e11, tol=1e-11, b=None, log=None):
         m = max(2, min(m, int(np.ceil(np.arccosh(tgt ** (1.0 / R)) / np.arccosh(xk)))))
         if stats["block_products"] + R * m > MAX_PRODUCTS:
             return None  # work budget: costlier than the syevd it replaces
-        for _ in range(R):
+        for _r in range(R):
             Y = cheb_filter(lambda X: C @ X, Y, m, lo, cut, up)
             stats["block_products"] += m
             try:
-                for _ in range(2):
+                # one CholeskyQR pass between rounds while the round amplified the top by <= 1e7, two before Rayleigh-Ritz
+                for _ in range(2 if (_r + 1 == R or np.cosh(m * np.arccosh(xtop)) > 1e7) else 1):
                     Rm = np.linalg.cholesky(Y.T @ Y).T
                     Y = np.linalg.solve(Rm.T, Y.T).T
             except np.linalg.LinAlgError:
