@@ -66,10 +66,10 @@ typedef enum srb_value_mode { SRB_VALUES_COMPACT = 0, SRB_VALUES_FAITHFUL = 1 } 
  *                  counts; bit-identical f32 on the device). Pays only when the link, not the host, is the bottleneck:
  *                  on the 16-core bench host it is slower than HOST_PACK (measured, profiles/), so AUTO never picks it
  *   HOST_PACK_ADAPTIVE  HOST_PACK, and a chunk's values are packed only while the host is ahead of the link (the staging
- *                  slot's previous DMA is still in flight), so the two stay balanced. Not yet measured (round 2).
+ *                  slot's previous DMA is still in flight), so the two stay balanced (upload at the bench size: 147-168 ms).
  *   HOST_PACK_DELTA  HOST_PACK with the sorted indices of each line delta-coded to ONE byte per entry (gap to the previous
  *                  index; gaps >= 255, line starts beyond 254 and non-canonical pairs escape to a side list), rebuilt
- *                  exactly on the device. Host coder tested on the CPU; device decode not yet measured (round 2).
+ *                  exactly on the device (upload at the bench size: 147-155 ms against 171-180 for HOST_PACK, 330 raw).
  *   BALANCED       every 4 M-entry chunk is either packed on the host (indices: DELTA codes, or HOST_PACK narrowing when the
  *                  offsets cannot be trusted; f32 counts: u8 / u16 where lossless) or sent raw and narrowed on the device —
  *                  packed exactly when the copies already queued on the link take at least as long as packing the chunk

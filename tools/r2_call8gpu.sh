@@ -1,7 +1,7 @@
 #!/bin/bash
-# round 2, call 10 (8 GPUs): N-GPU == 1-GPU == oracle parity check at world 8 (log kept), bench at N = 8 with every leg
+# round 2, call 15 (8 GPUs, final state): N-GPU == 1-GPU == oracle parity check at world 8 (log kept), bench at N = 8 with every leg
 mkdir -p gpurun_out
-S=gpurun_out/c10_summary.txt
+S=gpurun_out/c15_summary.txt
 : > $S
 nvidia-smi -L | wc -l >> $S; nproc >> $S; free -g | head -2 >> $S
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29681 tests/multigpu_check.py > gpurun_out/r02_multigpu8.log 2>&1; echo "multigpu_check(8) rc=$? $(grep 'MULTIGPU OK' gpurun_out/r02_multigpu8.log)" >> $S
