@@ -22,6 +22,7 @@ struct NcclApi {
     int (*CommInitRank)(nccl_comm *, int, nccl_uid, int) = nullptr;
     int (*CommDestroy)(nccl_comm) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 
@@ -37,8 +38,9 @@ static NcclApi &nccl() {
         api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
         api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
         api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+        api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
         api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
-        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce)
+        if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather)
             throw Error(SRB_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
     }
     return api;
@@ -62,6 +64,13 @@ void allreduce_u64_sum(srb_ctx *ctx, uint64_t *d, size_t n) { allreduce(ctx, d, 
 void allreduce_f64_sum(srb_ctx *ctx, double *d, size_t n) { allreduce(ctx, d, n, NCCL_FLOAT64, NCCL_SUM); }
 void allreduce_f64_min(srb_ctx *ctx, double *d, size_t n) { allreduce(ctx, d, n, NCCL_FLOAT64, NCCL_MIN); }
 void allreduce_f64_max(srb_ctx *ctx, double *d, size_t n) { allreduce(ctx, d, n, NCCL_FLOAT64, NCCL_MAX); }
+
+// in place: rank r's `count` doubles sit at buf + r * count on entry; on exit every rank holds all nranks * count
+void allgather_f64(srb_ctx *ctx, cudaStream_t stream, double *buf, size_t count) {
+    if (ctx->nranks <= 1 || count == 0) return;
+    SRB_REQUIRE(ctx->comm, SRB_ERR_NCCL, "communicator not initialised");
+    SRB_NCCL(nccl().AllGather(buf + (size_t)ctx->rank * count, buf, count, NCCL_FLOAT64, (nccl_comm)ctx->comm, stream));
+}
 
 void comm_destroy(srb_ctx *ctx) {
     if (ctx->comm) nccl().CommDestroy((nccl_comm)ctx->comm);

@@ -244,6 +244,7 @@ void allreduce_u64_sum(srb_ctx *ctx, uint64_t *d_buf, size_t n);
 void allreduce_f64_sum(srb_ctx *ctx, double *d_buf, size_t n);
 void allreduce_f64_min(srb_ctx *ctx, double *d_buf, size_t n);
 void allreduce_f64_max(srb_ctx *ctx, double *d_buf, size_t n);
+void allgather_f64(srb_ctx *ctx, cudaStream_t stream, double *d_buf, size_t count_per_rank);
 void comm_destroy(srb_ctx *ctx);
 void eig_destroy(srb_ctx *ctx);
 

@@ -454,6 +454,15 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
 
     // ---- 2./3. filter + Rayleigh-Ritz ----
     SRB_LAUNCH(fill_random_kernel, (unsigned)std::min<size_t>((db + 255) / 256, 4096), 256, 0, es, Y, (uint64_t)db, 0xC4EB5EEDull);
+    // column shards of the filter (row-sharded jobs only; every rank reaches this point with the same matrix and the same
+    // decisions: the Lanczos bounds, CholeskyQR and Rayleigh-Ritz steps are replicated and deterministic)
+    static const bool shard_off = [] {
+        const char *e = getenv("SRB_CHFSI_SHARD");
+        return e && e[0] == '0';
+    }();
+    const bool shard = !shard_off && ctx->nranks > 1 && ctx->comm && b % (uint32_t)ctx->nranks == 0 && b / (uint32_t)ctx->nranks >= 8;
+    const uint32_t shard_cols = shard ? b / (uint32_t)ctx->nranks : b;
+    const uint32_t shard_col0 = shard ? (uint32_t)ctx->rank * shard_cols : 0;
     const size_t chol_smem = 8 * (size_t)b * (b + 1) / 2;
     // SRB_CHFSI_CHOL=own selects the single-CTA kernel (measured SLOWER than cusolverDnDpotrf in its unblocked form: 0.38 vs
     // 0.2 ms at b = 192 — one latency-bound column at a time; kept for a blocked rewrite)
@@ -500,15 +509,20 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
             // scaled Chebyshev recurrence (Zhou & Saad): Y_1 = (s1/e) Cs Y_0 ; Y_{i+1} = (2 s_{i+1}/e) Cs Y_i - s_i s_{i+1} Y_{i-1}
             const double sigma1 = e / (up - c);
             double sigma = sigma1, a1 = sigma1 / e;
-            SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)d, &a1, Cs, (int)d, Y, (int)d, &zero, Yb, (int)d));
+            // The filter acts on every column independently. In a row-sharded job the correlation matrix is replicated
+            // bit for bit (allreduced), so each rank filters its own b / nranks columns and the block is allgathered once
+            // per round (2.5 MB over NVLink) instead of every rank filtering all b columns.
+            const size_t co = (size_t)shard_col0 * d;
+            SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)shard_cols, (int)d, &a1, Cs, (int)d, Y + co, (int)d, &zero, Yb + co, (int)d));
             double *Yp = Y, *Yc = Yb;
             for (int i = 2; i <= m_use; ++i) {
                 const double sn = 1.0 / (2.0 / sigma1 - sigma), al = 2.0 * sn / e, be = -sigma * sn;
-                SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)b, (int)d, &al, Cs, (int)d, Yc, (int)d, &be, Yp, (int)d));
+                SRB_CUBLAS(cublasDgemm(bl, CUBLAS_OP_N, CUBLAS_OP_N, (int)d, (int)shard_cols, (int)d, &al, Cs, (int)d, Yc + co, (int)d, &be, Yp + co, (int)d));
                 std::swap(Yp, Yc);
                 sigma = sn;
             }
             st.block_products += m_use;
+            if (shard_cols != b) allgather_f64(ctx, es, Yc, (size_t)shard_cols * d);
             if (Yc != Y) std::swap(Y, Yb);  // Y = filtered block, Yb = scratch
             trace.mark(1);
             // CholeskyQR: one pass leaves an orthogonality error of ~eps * cond(Y)^2. Before Rayleigh-Ritz the block must be
