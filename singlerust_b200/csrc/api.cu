@@ -284,8 +284,10 @@ int32_t srb_ctx_destroy(srb_ctx *ctx) {
     if (ctx->up_ring) cudaFreeHost(ctx->up_ring);
     for (int i = 0; i < srb_ctx::kUpSlots; ++i)
         if (ctx->up_ev[i]) cudaEventDestroy(ctx->up_ev[i]);
-    for (int i = 0; i < srb_ctx::kUpChunkEvents; ++i)
+    for (int i = 0; i < srb_ctx::kUpChunkEvents; ++i) {
         if (ctx->up_cev[i]) cudaEventDestroy(ctx->up_cev[i]);
+        if (ctx->up_sev[i]) cudaEventDestroy(ctx->up_sev[i]);
+    }
     for (int i = 0; i < ST_COUNT; ++i) {
         cudaEventDestroy(ctx->ev0[i]);
         cudaEventDestroy(ctx->ev1[i]);

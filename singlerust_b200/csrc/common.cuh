@@ -130,7 +130,7 @@ struct srb_ctx {
     bool up_ev_used[kUpSlots] = {};
     // per-chunk completion events of the balanced upload (upload.cu: upload_balanced): how far the link is behind the host
     static constexpr int kUpChunkEvents = 16;
-    cudaEvent_t up_cev[kUpChunkEvents] = {};
+    cudaEvent_t up_cev[kUpChunkEvents] = {}, up_sev[kUpChunkEvents] = {};  // end / start of a chunk's copies
     int last_upload_chunks = 0, last_upload_idx_packed = 0, last_upload_val_packed = 0;  // what the balanced upload chose
 };
 

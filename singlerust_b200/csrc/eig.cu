@@ -448,6 +448,23 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         if (!have_k && cw >= (double)k / d) lamk = ritz[i], have_k = true;
         if (!have_cut && cw >= 0.8 * b / d) cut = ritz[i], have_cut = true;
     }
+    {
+        // The step function can cross k / d one Ritz value too early; an optimistic lamk makes the first outer round
+        // under-filter (residual a few 1e-11, a second Rayleigh-Ritz step). The midpoint-rule CDF from the top, linearly
+        // interpolated between the Ritz values, is smoother: take the lower of the two estimates.
+        const double p = (double)k / d;
+        double acc = 0.0, c_prev = 0.0, t_prev = up, q = ritz[0];
+        bool found = false;
+        for (int i = L - 1; i >= 0; --i) {  // nodes from the top; (c, t) = (CDF from the top at the node, Ritz value)
+            const double w = S[(size_t)0 * L + i] * S[(size_t)0 * L + i], t = ritz[i], c = acc + 0.5 * w;
+            if (!found && p <= c) {
+                q = c > c_prev ? t_prev + (p - c_prev) / (c - c_prev) * (t - t_prev) : t;
+                found = true;
+            }
+            c_prev = c, t_prev = t, acc += w;
+        }
+        lamk = std::min(lamk, q);
+    }
     cut = std::min(cut, ritz[L - 1] - 0.02 * span);
     cut = std::max(cut, lo + 0.05 * span);
     lamk = std::max(lamk, cut + 0.01 * span);
@@ -489,9 +506,9 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
         const double xtop = std::max((up - c) / e, 1.0 + 1e-12), xk = std::max((lamk - c) / e, 1.0 + 1e-9);
         const int m = (int)std::max(2.0, std::min((double)kMaxDegree, std::floor(std::acosh(kAmpCap) / std::acosh(xtop))));
         const double amp = std::cosh(m * std::acosh(xk));
-        // a later outer round only tops up what the last Rayleigh-Ritz step showed missing (with a margin of 10): a residual
-        // of 3e-11 against the 1e-11 bound costs ~10 more block products, not a second full filter
-        const double target_now = outer == 0 ? kTarget : std::min(kTarget, std::max(1e2, 10.0 * st.max_residual / kTol));
+        // a later outer round only tops up what the last Rayleigh-Ritz step showed missing (with a margin of 1e3): a residual
+        // of 3e-11 against the 1e-11 bound costs ~18 more block products, not a second full filter
+        const double target_now = outer == 0 ? kTarget : std::min(kTarget, std::max(1e3, 1e3 * st.max_residual / kTol));
         int rounds = (int)std::ceil(std::log(target_now) / std::log(std::max(amp, 1.0001)));
         rounds = std::max(1, std::min(rounds, outer == 0 ? 3 : kMaxRounds));
         // the smallest degree that reaches the target in exactly `rounds` rounds (a ceil() on the round count would
@@ -564,7 +581,11 @@ static bool chfsi_topk(srb_ctx *ctx, cublasHandle_t bl, cusolverDnHandle_t so, c
             if (!std::isfinite(hth[j])) return false;
         st.max_residual = rmax / std::max(fabs(hth[b - 1]), 1e-300);
         converged = st.max_residual <= kTol;
-        cut = hth[0], lamk = hth[b - k], up = std::max(up, hth[b - 1]);
+        // the block's smallest Ritz value raises the cut when the first one left more than b eigenvalues above it; it only
+        // lowers it when the k-th Ritz value shows the cut sat above wanted eigenvalues (a badly converged last vector has a
+        // Ritz value deep inside the bulk, which would blunt the next filter)
+        lamk = hth[b - k], up = std::max(up, hth[b - 1]);
+        cut = lamk <= cut ? hth[0] : std::max(cut, hth[0]);
         if (!(cut > lo)) lo = cut - 0.05 * (up - cut);
     }
     ctx->last_eig_products = st.block_products, ctx->last_eig_outer = st.outer, ctx->last_eig_residual = st.max_residual;

@@ -348,8 +348,10 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
     const size_t val_bytes = values ? (chunk * (val_pageable ? vsz : 2) + 255) & ~size_t(255) : 0;
     const size_t slot_bytes = idx_bytes + val_bytes;
     ensure_upload_ring(c, slot_bytes * srb_ctx::kUpSlots);
-    for (int i = 0; i < srb_ctx::kUpChunkEvents; ++i)
-        if (!c->up_cev[i]) SRB_CUDA(cudaEventCreateWithFlags(&c->up_cev[i], cudaEventDisableTiming));
+    for (int i = 0; i < srb_ctx::kUpChunkEvents; ++i) {
+        if (!c->up_cev[i]) SRB_CUDA(cudaEventCreate(&c->up_cev[i]));  // timing enabled: the copies' own duration gives the link rate
+        if (!c->up_sev[i]) SRB_CUDA(cudaEventCreate(&c->up_sev[i]));
+    }
     Buf dpk = pw < 4 ? dev_alloc(s, n * pw) : Buf();            // packed index codes (pw = 4 lands in d_idx directly)
     Buf draw = dev_alloc(s, chunk * (size_t)width);              // raw index chunk, narrowed right after its copy
     Buf dvpk = vals_packable ? dev_alloc(s, nchunks * chunk * 2) : Buf();
@@ -361,13 +363,26 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
     std::vector<uint64_t> cum_bytes(nchunks + 1, 0);  // bytes enqueued up to and including chunk i - 1
     double t_idx = 0.0, t_val = 0.0;                  // running estimates of the packing time of one chunk (ms)
     double acc_raw = 0.0, acc_val = 0.0;              // dithering accumulators of the raw-index / packed-value fractions
+    uint64_t n_rate = 0;                              // link-rate samples taken
     int slot_use = 0;
-    const double rate = link_rate_bytes_per_ms();
+    // link rate: SRB_LINK_GBS (default 50) until the first chunks have completed, then the running mean of what the copies
+    // of this upload really achieved (bytes / duration between the chunk's start and end events). With 8 GPUs uploading at
+    // once each gets ~18 GB/s of the host's memory and PCIe fabric, not 50, and a model that assumes 50 sends too much raw.
+    const bool rate_fixed = getenv("SRB_LINK_GBS") != nullptr;
+    double rate = link_rate_bytes_per_ms();
     uint64_t ci = 0;
     for (uint64_t o = 0; o < n; o += chunk, ++ci) {
         const uint64_t len = std::min<uint64_t>(chunk, n - o);
         // retire completed chunks (keeps the per-chunk events reusable; the decision itself is model-based, see below)
-        while (done < ci && cudaEventQuery(c->up_cev[done % srb_ctx::kUpChunkEvents]) == cudaSuccess) ++done;
+        while (done < ci && cudaEventQuery(c->up_cev[done % srb_ctx::kUpChunkEvents]) == cudaSuccess) {
+            float ms = 0.f;
+            const uint64_t cb = cum_bytes[done + 1] - cum_bytes[done];
+            if (!rate_fixed && cb && cudaEventElapsedTime(&ms, c->up_sev[done % srb_ctx::kUpChunkEvents], c->up_cev[done % srb_ctx::kUpChunkEvents]) == cudaSuccess && ms > 0.f) {
+                const double r = (double)cb / (double)ms;
+                rate = n_rate++ == 0 ? r : 0.75 * rate + 0.25 * r;
+            }
+            ++done;
+        }
         (void)cudaGetLastError();  // cudaErrorNotReady is not an error here
         done_bytes = cum_bytes[done];
         // Rate model. Per chunk of `len` entries: packing the indices costs the host t_idx (measured, running mean, with
@@ -403,6 +418,11 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
             h_idx = (char *)c->up_ring + slot_bytes * slot, h_val = h_idx + idx_bytes;
         }
         uint64_t bytes = 0;
+        if (ci >= (uint64_t)srb_ctx::kUpChunkEvents && done + srb_ctx::kUpChunkEvents <= ci) {
+            // the events about to be reused belong to a chunk that has not been seen complete yet
+            SRB_CUDA(cudaEventSynchronize(c->up_cev[ci % srb_ctx::kUpChunkEvents]));
+            done = ci - srb_ctx::kUpChunkEvents + 1;
+        }
         // ---- indices ----
         if (pack_idx) {
             const double t0 = host_now_ms();
@@ -411,6 +431,7 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
             const double dt = (host_now_ms() - t0) * (double)chunk / (double)len;
             t_idx = t_idx == 0.0 ? dt : 0.5 * t_idx + 0.5 * dt;
             char *dst = pw < 4 ? dpk->as<char>() + o * pw : (char *)(d_idx + o);
+            SRB_CUDA(cudaEventRecord(c->up_sev[ci % srb_ctx::kUpChunkEvents], s));  // after packing: the copies' own duration
             SRB_CUDA(cudaMemcpyAsync(dst, h_idx, len * pw, cudaMemcpyHostToDevice, s));
             if (pw == 2) SRB_LAUNCH((narrow_index_kernel<uint16_t>), grid_for(c, len), 256, 0, s, dpk->as<uint16_t>() + o, d_idx + o, len, bound, d_flags);
             bytes += len * pw;
@@ -422,6 +443,7 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
                 host_copy_parallel(src, h_idx, len * width, nthreads);
                 src = h_idx;
             }
+            SRB_CUDA(cudaEventRecord(c->up_sev[ci % srb_ctx::kUpChunkEvents], s));
             SRB_CUDA(cudaMemcpyAsync(draw->p, src, len * width, cudaMemcpyHostToDevice, s));
             if (width == 8) SRB_LAUNCH((narrow_index_kernel<uint64_t>), grid_for(c, len), 256, 0, s, draw->as<uint64_t>(), d_idx + o, len, bound, d_flags);
             else SRB_LAUNCH((narrow_index_kernel<uint32_t>), grid_for(c, len), 256, 0, s, draw->as<uint32_t>(), d_idx + o, len, bound, d_flags);
@@ -463,11 +485,6 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
             const int slot = (slot_use - 1) % srb_ctx::kUpSlots;
             SRB_CUDA(cudaEventRecord(c->up_ev[slot], s));
             c->up_ev_used[slot] = true;
-        }
-        if (ci >= (uint64_t)srb_ctx::kUpChunkEvents && done + srb_ctx::kUpChunkEvents <= ci) {
-            // the event about to be reused belongs to a chunk that has not been seen complete yet
-            SRB_CUDA(cudaEventSynchronize(c->up_cev[ci % srb_ctx::kUpChunkEvents]));
-            done = ci - srb_ctx::kUpChunkEvents + 1;
         }
         SRB_CUDA(cudaEventRecord(c->up_cev[ci % srb_ctx::kUpChunkEvents], s));
         enq_bytes += bytes, link += bytes;

@@ -45,6 +45,19 @@ def krylov_bounds(C, rng, L):
     return th, S, beta
 
 
+def dos_quantile(th, w, up, p):
+    """Eigenvalue below which a fraction 1 - p of the spectrum lies, from Ritz values th (ascending) with weights w: CDF from
+    the top by the midpoint rule, linear interpolation between the nodes (eig.cu: dos_quantile)."""
+    t, ww = th[::-1], w[::-1]
+    c = np.cumsum(ww) - ww / 2
+    if p <= c[0]:
+        return up - (up - t[0]) * p / c[0]
+    for i in range(len(t) - 1):
+        if c[i] <= p < c[i + 1]:
+            return t[i] + (p - c[i]) / (c[i + 1] - c[i]) * (t[i + 1] - t[i])
+    return t[-1]
+
+
 def block_width(d, k):
     return min(d // 4, ((max(3 * k, k + 96) + 31) // 32) * 32)
 
@@ -74,6 +87,9 @@ def chfsi_topk(C, k, seed=0, L=16, target=1e11, tol=1e-11, b=None, log=None):
             lamk, have_k = th[i], True
         if not have_cut and cw >= 0.8 * b / d:
             cut, have_cut = th[i], True
+    # the step function above can cross k / d one Ritz value too early (an optimistic lamk makes the first outer round
+    # under-filter); the midpoint-rule, linearly interpolated quantile is smoother: take the lower of the two
+    lamk = min(lamk, dos_quantile(th, S[0, :] ** 2, up, k / d))
     cut = max(min(cut, th[-1] - 0.02 * span), lo + 0.05 * span)
     lamk = max(lamk, cut + 0.01 * span)
     Y = rng.uniform(-1, 1, (d, b))
@@ -87,7 +103,7 @@ def chfsi_topk(C, k, seed=0, L=16, target=1e11, tol=1e-11, b=None, log=None):
         m = int(max(2, min(MAX_DEGREE, np.floor(np.arccosh(AMP_CAP) / np.arccosh(xtop)))))
         amp = np.cosh(m * np.arccosh(xk))
         # later outer rounds only top up what the last Rayleigh-Ritz step showed missing (x10 margin), eig.cu: target_now
-        tgt = target if outer == 0 else float(min(target, max(1e2, 10.0 * stats["max_residual"] / tol)))
+        tgt = target if outer == 0 else float(min(target, max(1e3, 1e3 * stats["max_residual"] / tol)))
         R = int(np.ceil(np.log(tgt) / np.log(max(amp, 1.0001))))
         R = max(1, min(R, 3 if outer == 0 else MAX_ROUNDS))
         # the smallest degree that reaches the target in exactly R rounds (eig.cu: m_use)
@@ -120,7 +136,11 @@ def chfsi_topk(C, k, seed=0, L=16, target=1e11, tol=1e-11, b=None, log=None):
         stats["max_residual"] = rel
         if rel <= tol:
             return tt[b - k:], Y[:, b - k:], stats
-        cut, lamk, up = tt[0], tt[b - k], max(up, tt[-1])
+        # the block's smallest Ritz value raises the cut when the first one left more than b eigenvalues above it; it only
+        # lowers it when the k-th Ritz value shows the cut sat above wanted eigenvalues (a badly converged last vector has a
+        # Ritz value deep inside the bulk, which would blunt the next filter)
+        lamk, up = tt[b - k], max(up, tt[-1])
+        cut = tt[0] if lamk <= cut else max(cut, tt[0])
         if not cut > lo:
             lo = cut - 0.05 * (up - cut)
     return None
