@@ -410,6 +410,9 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
             try_val = true;
             if (!probe) acc_val -= 1.0;
         }
+        // pageable values would have to be staged through the ring anyway (read 4 B + write 4 B per entry on the host):
+        // packing them (read 4 B + write 1 B) is the cheaper way to get them there
+        if (vstate != 0 && val_pageable) try_val = true;
         const bool need_slot = pack_idx || try_val || (values && val_pageable) || idx_pageable;
         char *h_idx = nullptr, *h_val = nullptr;
         if (need_slot) {
