@@ -34,6 +34,7 @@ extern "C" {
     pub fn srb_ctx_set_eig_mode(ctx: *mut srb_ctx, mode: i32) -> i32;      // 0 syevd, 1 chfsi
     pub fn srb_ctx_last_eig(ctx: *mut srb_ctx, solver: *mut i32, block_products: *mut i32, outer_iterations: *mut i32,
                             max_residual: *mut f64) -> i32;
+    pub fn srb_upload_mix(t_idx_ms: f64, t_val_ms: f64, len: u64, packed_index_bytes: i32, idx_width: i32, value_bytes: i32, link_gbs: f64, raw_index_fraction: *mut f64, packed_value_fraction: *mut f64) -> i32;
     pub fn srb_ctx_last_upload(ctx: *mut srb_ctx, h2d_bytes: *mut u64, host_packed: *mut i32) -> i32;
     pub fn srb_ctx_last_upload_chunks(ctx: *mut srb_ctx, chunks: *mut i32, index_chunks_packed: *mut i32, value_chunks_packed: *mut i32) -> i32;
     pub fn srb_ctx_synchronize(ctx: *mut srb_ctx) -> i32;

@@ -118,6 +118,13 @@ int32_t srb_host_delta_encode(const void *indices, const void *offsets, int32_t 
                               uint64_t bound, uint64_t chunk, int32_t nthreads, uint8_t *codes, uint64_t *esc_pos,
                               uint32_t *esc_val, uint64_t esc_cap, uint64_t *n_esc, int32_t *out_of_bounds);
 
+/* the rate model of the BALANCED upload, for testing (no GPU): with a measured packing time of t_idx_ms / t_val_ms per chunk of
+ * `len` entries and a link of link_gbs GB/s, the share of chunks whose indices should travel raw (idx_width bytes per entry
+ * instead of packed_index_bytes) and the share whose f32 values should be packed to one byte, so that host and link finish
+ * together. Returns 0, or -1 on a bad argument. */
+int32_t srb_upload_mix(double t_idx_ms, double t_val_ms, uint64_t len, int32_t packed_index_bytes, int32_t idx_width,
+                       int32_t value_bytes, double link_gbs, double *raw_index_fraction, double *packed_value_fraction);
+
 /* ---- context ------------------------------------------------------------------------------------ */
 int32_t srb_ctx_create(int32_t device, srb_ctx **out);
 int32_t srb_ctx_destroy(srb_ctx *ctx);

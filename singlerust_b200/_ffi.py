@@ -57,6 +57,7 @@ def lib() -> C.CDLL:
             "srb_ctx_set_value_mode": [vp, i32],
             "srb_ctx_set_upload_mode": [vp, i32],
             "srb_host_pack_indices": [vp, i32, u64, vp, i32, u64, i32, C.POINTER(i32)],
+            "srb_upload_mix": [f64, f64, u64, i32, i32, i32, f64, C.POINTER(f64), C.POINTER(f64)],
             "srb_ctx_last_upload": [vp, C.POINTER(u64), C.POINTER(i32)],
             "srb_ctx_last_upload_chunks": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
             "srb_ctx_set_eig_mode": [vp, i32],
@@ -167,6 +168,14 @@ def host_pack_values_f32(src: np.ndarray, dst_width: int, nthreads: int = 0):
     if lib().srb_host_pack_values_f32(_ptr(src), src.shape[0], _ptr(dst), dst_width, nthreads, C.byref(ok)) != 0:
         raise ValueError("srb_host_pack_values_f32: bad argument")
     return dst, bool(ok.value)
+
+
+def upload_mix(t_idx_ms, t_val_ms, n_entries, packed_index_bytes=1, idx_width=8, value_bytes=4, link_gbs=50.0):
+    """Rate model of the BALANCED upload (no GPU): (share of chunks with raw indices, share of chunks with packed values)."""
+    g, f = C.c_double(0.0), C.c_double(0.0)
+    if lib().srb_upload_mix(t_idx_ms, t_val_ms, n_entries, packed_index_bytes, idx_width, value_bytes, link_gbs, C.byref(g), C.byref(f)) != 0:
+        raise ValueError("srb_upload_mix: bad argument")
+    return g.value, f.value
 
 
 def kernel_launch_count() -> int:

@@ -196,6 +196,20 @@ void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads
     });
 }
 
+void upload_mix(double t_idx, double t_val, uint64_t len, int pw, int width, size_t vsz, int vstate, double rate, double *g_out, double *f_out) {
+    double g = 0.0, f = 0.0;
+    const double t_ki = (double)len * pw / rate, t_ri = (double)len * width / rate;
+    const double t_vr = vsz ? (double)len * (double)vsz / rate : 0.0, t_vp = vsz ? (double)len * (vstate == 2 ? 2 : 1) / rate : 0.0;
+    if (t_idx > 0.0) {
+        // host and link finish together when (1 - g) t_idx = (1 - g) t_k + g t_r
+        const double t_k = t_ki + t_vr, t_r = t_ri + t_vr;
+        if (t_idx > t_k) g = (t_idx - t_k) / (t_idx - t_k + t_r);
+        // spare host time: t_idx + f t_val = t_k - f (t_vr - t_vp)
+        else if (vstate && vsz == 4 && t_val > 0.0) f = std::min(1.0, (t_k - t_idx) / (t_val + t_vr - t_vp));
+    }
+    *g_out = g, *f_out = f;
+}
+
 // ---- count values: f32 -> u8 / u16 when that is lossless ------------------------------------------------------------
 // Raw counts are small non-negative integers stored as f32 (the common h5ad case). A chunk whose every value is an
 // integer in [0, 2^(8 dw)) travels as dw-byte integers. The test is bit-exact — the round trip through int32 must
@@ -362,6 +376,14 @@ extern "C" int32_t srb_host_delta_encode(const void *cols, const void *offs, int
         memcpy(esc_pos, esc.pos.data(), 8 * esc.pos.size());
         memcpy(esc_val, esc.val.data(), 4 * esc.val.size());
     }
+    return 0;
+}
+
+extern "C" int32_t srb_upload_mix(double t_idx_ms, double t_val_ms, uint64_t len, int32_t packed_index_bytes, int32_t idx_width,
+                                  int32_t value_bytes, double link_gbs, double *raw_index_fraction, double *packed_value_fraction) {
+    if (!raw_index_fraction || !packed_value_fraction || !(link_gbs > 0.0) || len == 0) return -1;
+    srb::upload_mix(t_idx_ms, t_val_ms, len, packed_index_bytes, idx_width, (size_t)value_bytes, value_bytes == 4 ? 1 : 0, link_gbs * 1e6,
+                    raw_index_fraction, packed_value_fraction);
     return 0;
 }
 

@@ -22,6 +22,13 @@ bool host_offsets_valid(const void *offs, int width, uint64_t nmajor, uint64_t n
 // codes for the entries [o, o + len) into dst[0 .. len), escapes appended to esc; returns true when any index >= bound
 bool host_delta_encode(const void *cols, const void *offs, int width, uint64_t nmajor, uint64_t o, uint64_t len, uint8_t *dst,
                        uint64_t bound, int nthreads, DeltaEscapes &esc);
+// The rate model of the BALANCED upload (upload.cu). Per chunk of `len` entries: packing the indices costs the host t_idx_ms
+// (measured) and the link len * pw bytes; raw costs the host nothing and the link len * width bytes; values travel raw
+// (vsz bytes) or packed (1 byte, 2 when vstate == 2) at a host cost of t_val_ms. *raw_index_fraction = the share of chunks
+// whose indices should go raw so that host and link finish together (0 when the host packs faster than the link drains);
+// *packed_value_fraction = the share whose values should be packed with the host time that is left over (0 otherwise).
+void upload_mix(double t_idx_ms, double t_val_ms, uint64_t len, int pw, int width, size_t vsz, int vstate, double link_bytes_per_ms,
+                double *raw_index_fraction, double *packed_value_fraction);
 // threaded memcpy (pageable host memory -> pinned staging ring)
 void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads);
 }  // namespace srb

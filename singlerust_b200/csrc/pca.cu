@@ -92,7 +92,9 @@ void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, dou
 // (Two cp.async.bulk-staged variants were measured in round 2 and removed: 8 warps sharing one tile, the row of an entry found
 // by binary search, a barrier per tile: 12.5 ms; row-owning consumer warps reading a shared-memory ring like K1, selection
 // bitmap in shared memory: 4.95 ms. This kernel with 8 loads per array in flight per lane: 4.3-4.4 ms. Staging the loads does
-// not help here because the stall is the dependent chain LUT -> (shift, 1/sd) -> store of the selected 7 %, not the stream.)
+// not help here because the stall is the dependent chain LUT -> (shift, 1/sd) -> store of the selected 7 %, not the stream.
+// Loading a value only after the LUT said its entry is selected (45 % of the value sectors instead of all): 4.06 vs 4.12 ms,
+// not kept.)
 template <typename VT>
 __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const uint16_t *__restrict__ lut,
@@ -143,9 +145,7 @@ __global__ void __launch_bounds__(256) densify_panels_kernel(const int64_t *__re
 }
 
 // default variant: register double buffer (SRB_DENSIFY_PIPE=0 selects the plain batched kernel above)
-// LAZY: the value of an entry is loaded only after the LUT said the entry is selected (7 % of the entries; at 32-byte sector
-// granularity that is ~45 % of the value array instead of all of it), at the price of one more dependent load in the chain
-template <typename VT, int kBatch, bool LAZY>
+template <typename VT, int kBatch>
 __global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_kernel(const int64_t *__restrict__ off, const uint32_t *__restrict__ idx,
                                                              const VT *__restrict__ val, const uint16_t *__restrict__ lut,
                                                              const float2 *__restrict__ shis,
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_
         for (int u = 0; u < kBatch; ++u) {
             const int64_t k = k0 + 32 * u;
             cc[u] = k < b ? idx[k] : 0xFFFFFFFFu;
-            if (!LAZY) vv[u] = k < b ? (float)val[k] : 0.f;
+            vv[u] = k < b ? (float)val[k] : 0.f;
         }
         uint4 *oh = reinterpret_cast<uint4 *>(Xh + r * dpad), *ol = reinterpret_cast<uint4 *>(Xl + r * dpad);
         for (uint32_t i = lane; i < nvec; i += 32) oh[i] = ch[i], ol[i] = cl[i];
@@ -187,15 +187,11 @@ __global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_
             for (int u = 0; u < kBatch; ++u) {
                 const int64_t k = kn + 32 * u;
                 cn[u] = k < b ? idx[k] : 0xFFFFFFFFu;
-                if (!LAZY) vn[u] = k < b ? (float)val[k] : 0.f;
+                vn[u] = k < b ? (float)val[k] : 0.f;
             }
             uint32_t pp[kBatch];
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) pp[u] = cc[u] != 0xFFFFFFFFu ? (uint32_t)lut[cc[u]] : 0xFFFFu;
-            if (LAZY) {
-#pragma unroll
-                for (int u = 0; u < kBatch; ++u) vv[u] = pp[u] != 0xFFFFu ? (float)val[k0 + 32 * u] : 0.f;
-            }
 #pragma unroll
             for (int u = 0; u < kBatch; ++u) {
                 const uint32_t p = pp[u];
@@ -208,10 +204,7 @@ __global__ void __launch_bounds__(256, kBatch == 4 ? 4 : 3) densify_panels_pipe_
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                cc[u] = cn[u];
-                if (!LAZY) vv[u] = vn[u];
-            }
+            for (int u = 0; u < kBatch; ++u) cc[u] = cn[u], vv[u] = vn[u];
         }
         __syncwarp();
     }
@@ -504,16 +497,10 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
             const char *e = getenv("SRB_DENSIFY_BATCH");
             return (e && atoi(e) == 4) ? 0 : 1;  // 8 loads per array in flight per lane: 4.30-4.38 ms against 4.64 for 4 (measured)
         }();
-        static const int lazy = [] {
-            const char *e = getenv("SRB_DENSIFY_LAZY");
-            return (e && e[0] == '1') ? 1 : 0;
-        }();
-        if (m->vdtype == SRB_F32 && pipe && batch8 && lazy) {
-            SRB_LAUNCH((densify_panels_pipe_kernel<float, 8, true>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
-        } else if (m->vdtype == SRB_F32 && pipe && batch8) {
-            SRB_LAUNCH((densify_panels_pipe_kernel<float, 8, false>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        if (m->vdtype == SRB_F32 && pipe && batch8) {
+            SRB_LAUNCH((densify_panels_pipe_kernel<float, 8>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else if (m->vdtype == SRB_F32 && pipe) {
-            SRB_LAUNCH((densify_panels_pipe_kernel<float, 4, false>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+            SRB_LAUNCH((densify_panels_pipe_kernel<float, 4>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else if (m->vdtype == SRB_F32) {
             SRB_LAUNCH((densify_panels_kernel<float>), grid, 256, smem, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), lut16->as<uint16_t>(), shis->as<float2>(), zc_h->as<__half>(), zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
         } else {
@@ -614,7 +601,7 @@ static void stream_densify(srb_pca_stream *ps, srb_mat *m, Buf &Xh, Buf &Xl) {
     if (!n) return;
     const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)c->sm_count * 8 * 4);
     if (m->vdtype == SRB_F32)
-        SRB_LAUNCH((densify_panels_pipe_kernel<float, 8, false>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
+        SRB_LAUNCH((densify_panels_pipe_kernel<float, 4>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<float>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
     else
         SRB_LAUNCH((densify_panels_kernel<double>), grid, 256, 0, s, m->st->offsets->as<int64_t>(), m->st->indices->as<uint32_t>(), m->values->as<double>(), ps->lut16->as<uint16_t>(), ps->shis->as<float2>(), ps->zc_h->as<__half>(), ps->zc_l->as<__half>(), n, dpad, Xh->as<__half>(), Xl->as<__half>());
 }

@@ -391,14 +391,8 @@ static uint64_t upload_balanced(srb_ctx *c, const void *indices, int width, uint
         //     g = (t_idx - t_k) / (t_idx - t_k + t_r)        t_k, t_r = link time of a packed / raw chunk (indices + values)
         // of the chunks goes raw (g = 0 when the host packs faster than the link drains). Only when the host is FASTER than
         // the link is the spare host time spent on packing values, for the fraction f of chunks that equalises the two.
-        const double t_ki = (double)len * pw / rate, t_ri = (double)len * width / rate;
-        const double t_vr = values ? (double)len * vsz / rate : 0.0, t_vp = values ? (double)len * (vstate == 2 ? 2 : 1) / rate : 0.0;
         double g = 0.0, f = 0.0;
-        if (t_idx > 0.0) {
-            const double t_k = t_ki + t_vr, t_r = t_ri + t_vr;
-            if (t_idx > t_k) g = (t_idx - t_k) / (t_idx - t_k + t_r);
-            else if (vstate && t_val > 0.0) f = std::min(1.0, (t_k - t_idx) / (t_val + t_vr - t_vp));
-        }
+        upload_mix(t_idx, t_val, len, pw, width, values ? vsz : 0, vstate, rate, &g, &f);
         // every 32nd chunk is packed regardless, so a pessimistic first timing (cold pages, pool start-up) cannot lock
         // the upload into the raw mode
         const bool probe = ci % 32 == 0;

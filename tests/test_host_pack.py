@@ -257,3 +257,28 @@ def test_delta_fuzz_against_both_decoders():
         np.testing.assert_array_equal(warp_decode_emulation(off, codes, pos, val), idx)
 
     run()
+
+
+def test_balanced_upload_rate_model():
+    """srb_upload_mix: host and link must finish together. Chunk of 4 M entries, u64 indices -> 1-byte codes, f32 values."""
+    from singlerust_b200 import _ffi
+    n = 1 << 22
+    link = 50.0                                   # GB/s -> bytes per ms = 5e7
+    t_k = n * (1 + 4) / (link * 1e6)              # packed indices + raw values
+    t_r = n * (8 + 4) / (link * 1e6)
+    # a fast host (packing takes half of what the link needs for the packed chunk): nothing goes raw, values get packed
+    g, f = _ffi.upload_mix(0.5 * t_k, 0.1, n, link_gbs=link)
+    assert g == 0.0 and 0.0 < f <= 1.0
+    host, linkt = 0.5 * t_k + f * 0.1, t_k - f * n * 3 / (link * 1e6)
+    assert f == 1.0 or abs(host - linkt) < 1e-9   # equalised unless every chunk is already packed
+    # a slow host (8 ranks sharing the cores): most chunks go raw, and both sides finish together
+    t_idx = 8.0 * t_k
+    g, f = _ffi.upload_mix(t_idx, 0.1, n, link_gbs=link)
+    assert f == 0.0 and 0.5 < g < 1.0
+    assert abs((1 - g) * t_idx - ((1 - g) * t_k + g * t_r)) < 1e-9
+    # a slower link (8 GPUs uploading at once) moves the balance back towards packing
+    g18, _ = _ffi.upload_mix(t_idx, 0.1, n, link_gbs=18.0)
+    assert g18 < g
+    # f64 values are never packed; nothing measured yet -> pack (the first chunk is the probe)
+    assert _ffi.upload_mix(0.01, 0.1, n, value_bytes=8, link_gbs=link)[1] == 0.0
+    assert _ffi.upload_mix(0.0, 0.0, n, link_gbs=link) == (0.0, 0.0)
