@@ -229,7 +229,8 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
              PcaOut out);
 void densify_selected_f64(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, double *d_out, uint64_t row0, uint64_t nrows);
 // gram_tc.cu (tcgen05)
-void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G);
+// d_used: the leading columns of the panels that hold selected genes (0 = all dpad); the rest is zero padding
+void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G, uint32_t d_used = 0);
 // scores = Z' W - 1 bias^T (bias[kpad]: the rank-one correction of the sparse panel shift, zeros when every column is centred)
 void scores_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, const double *W,
                     uint32_t kpad, uint32_t k, const double *bias, double *scores);

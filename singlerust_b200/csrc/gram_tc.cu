@@ -294,9 +294,9 @@ static CUtensorMap panel_map(const __half *X, uint64_t n, uint32_t dpad) {
 }  // namespace tc
 
 CUtensorMap gram_panel_map(const __half *X, uint64_t n, uint32_t dpad) { return tc::panel_map(X, n, dpad); }
-void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G);  // gram_tc2.cu
+void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G, uint32_t d_used);  // gram_tc2.cu
 
-void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G) {
+void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G, uint32_t d_used) {
     using namespace tc;
     if (n == 0) return;
     {
@@ -307,7 +307,7 @@ void gram_tcgen05(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, 
             use_pair = (e && e[0] == '0') ? 0 : 1;
         }
         if (use_pair) {
-            gram_tcgen05_pair(ctx, Xh, Xl, n, dpad, G);
+            gram_tcgen05_pair(ctx, Xh, Xl, n, dpad, G, d_used);
             return;
         }
     }

@@ -31,7 +31,8 @@ constexpr uint32_t FLUSH_CELLS = 8192;  // fp32 register sums are folded into fp
 constexpr uint32_t THREADS = 320;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((TN >> 3) << 17) | ((TM >> 4) << 24);
+// instruction descriptor: D = f32, A = B = f16, both MN-major, M = 256 (the pair), N = n (256, or less in the last tile column)
+__host__ __device__ constexpr uint32_t idesc_n(uint32_t n) { return (1u << 4) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((TM >> 4) << 24); }
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // cute::Sm100MmaPeerBitMask: address of the even (leader) CTA's copy
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -111,6 +112,7 @@ struct Params {
     uint32_t kblocks_total;
     double *partial;     // [items][256][256]
     uint32_t chunk_kblocks;  // k-blocks (of 64 cells) per TMEM accumulation chunk
+    uint32_t last_tj, last_n;  // tiles of the last tile column only need N = last_n (< 256) accumulator columns
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -131,6 +133,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
     const uint32_t per = (p.kblocks_total + p.ksplit - 1) / p.ksplit;
     const uint32_t kb0 = min(ks * per, p.kblocks_total), kb1 = min(kb0 + per, p.kblocks_total);
     const uint32_t nkb = kb1 - kb0;
+    const uint32_t n_cols = tij.y == p.last_tj ? p.last_n : TN;  // accumulator columns this tile really needs
+    const uint32_t idesc = idesc_n(n_cols);
     const uint32_t CHUNK_KBLOCKS = p.chunk_kblocks;
     const uint32_t FLUSH_CHUNKS = max(1u, FLUSH_CELLS / (CHUNK_KBLOCKS * BK));
     const uint32_t nchunks = (nkb + CHUNK_KBLOCKS - 1) / CHUNK_KBLOCKS;
@@ -166,7 +170,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 #pragma unroll
                 for (uint32_t b = 0; b < HALF_BOXES; ++b) {
                     const int32_t ga = (int32_t)(tij.x * TM + rank * 128 + b * 64);
-                    const int32_t gb = (int32_t)(tij.y * TN + rank * 128 + b * 64);
+                    const int32_t gb = (int32_t)(tij.y * TN + rank * (n_cols / 2) + b * 64);  // this CTA's N / 2 columns of B
                     tma_load_2d_pair(a_hi + b * BOX_BYTES, &map_hi, full_bar + 8 * s, ga, row);
                     tma_load_2d_pair(a_lo + b * BOX_BYTES, &map_lo, full_bar + 8 * s, ga, row);
                     tma_load_2d_pair(b_hi + b * BOX_BYTES, &map_hi, full_bar + 8 * s, gb, row);
@@ -198,9 +202,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
                             const uint64_t dah = make_desc_mn_sw128(a_hi + ko), dal = make_desc_mn_sw128(a_lo + ko);
                             const uint64_t dbh = make_desc_mn_sw128(b_hi + ko), dbl = make_desc_mn_sw128(b_lo + ko);
                             const uint32_t first = (kb == c * CHUNK_KBLOCKS && kk == 0) ? 0u : 1u;
-                            tc_mma_pair(d_tmem, dal, dbh, IDESC, first);
-                            tc_mma_pair(d_tmem, dah, dbl, IDESC, 1u);
-                            tc_mma_pair(d_tmem, dah, dbh, IDESC, 1u);
+                            tc_mma_pair(d_tmem, dal, dbh, idesc, first);
+                            tc_mma_pair(d_tmem, dah, dbl, idesc, 1u);
+                            tc_mma_pair(d_tmem, dah, dbh, idesc, 1u);
                         }
                         tc_commit_pair(empty_bar + 8 * s);
                         if (kb + 1 == kend) tc_commit_pair(tfull_bar + 8 * as);
@@ -286,7 +290,7 @@ __global__ void gram_reduce2_kernel(const double *__restrict__ partial, const ui
 
 CUtensorMap gram_panel_map(const __half *X, uint64_t n, uint32_t dpad);  // gram_tc.cu
 
-void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G) {
+void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_t n, uint32_t dpad, double *G, uint32_t d_used) {
     using namespace tc2;
     if (n == 0) return;
     cudaStream_t s = ctx->stream;
@@ -309,6 +313,18 @@ void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_
     p.ksplit = ksplit;
     p.kblocks_total = kblocks;
     p.partial = partial->as<double>();
+    {
+        // the columns beyond d_used are padding: the tiles of the last tile column run the MMA with N = what is needed,
+        // rounded to 32 (each CTA of the pair supplies N / 2 columns, a multiple of 16) — 208 instead of 256 at d = 2000
+        static const int trim = [] {
+            const char *e = getenv("SRB_GRAM_TRIM");
+            return (e && e[0] == '0') ? 0 : 1;
+        }();
+        const uint32_t used = d_used ? std::min(d_used, dpad) : dpad;
+        const uint32_t rem = used - (NT - 1) * TN;  // columns of the last tile column that hold selected genes
+        p.last_tj = NT - 1;
+        p.last_n = trim ? std::max<uint32_t>(32, std::min<uint32_t>(TN, (rem + 31) / 32 * 32)) : TN;
+    }
     {
         static int chunk = -1;
         if (chunk < 0) {

@@ -513,7 +513,7 @@ void pca_run(srb_mat *m, const uint32_t *d_sel, uint64_t n_sel, uint64_t k, bool
     {
         StageTimer t(c, ST_GRAM);
         if (gram_mode == 0) {
-            gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, G->as<double>());
+            gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, G->as<double>(), (uint32_t)n_sel);
         } else if (n) {
             const uint32_t nt = dpad / GT;
             const uint32_t ntiles = nt * (nt + 1) / 2;
@@ -683,7 +683,7 @@ int32_t srb_pca_stream_push_gram(srb_pca_stream *ps, srb_mat *chunk) {
         Buf Gc = dev_zeros(s, 8 * (size_t)dpad * dpad);
         // a chunk smaller than one tensor-core tile of cells goes through the fp64 CUDA-core Gram (exact, and tiny)
         if (ps->gram_mode == 0 && n >= 256) {
-            gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, Gc->as<double>());
+            gram_tcgen05(c, Xh->as<__half>(), Xl->as<__half>(), n, dpad, Gc->as<double>(), (uint32_t)ps->n_sel);
         } else {
             const uint32_t nt = dpad / GT;
             const uint32_t ntiles = nt * (nt + 1) / 2;
