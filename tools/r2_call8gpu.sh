@@ -6,7 +6,7 @@ S=gpurun_out/c15_summary.txt
 nvidia-smi -L | wc -l >> $S; nproc >> $S; free -g | head -2 >> $S
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29681 tests/multigpu_check.py > gpurun_out/r02_multigpu8.log 2>&1; echo "multigpu_check(8) rc=$? $(grep 'MULTIGPU OK' gpurun_out/r02_multigpu8.log)" >> $S
 grep -E "N vs 1 GPU|N GPUs vs oracle" gpurun_out/r02_multigpu8.log | cut -c1-400 >> $S
-timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29682 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; echo "bench n8 rc=$?" >> $S
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29682 bench.py --gpus 8 --steps 10 --warmup 3 --legs strong,xl --no-pageable > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; echo "bench n8 rc=$?" >> $S
 python - >> $S <<'PY'
 import json
 try:
