@@ -456,14 +456,22 @@ def stage_rooflines(args, n, nnz, mean_stage):
 
 
 def gram_executed_flops(n, d):
-    """Flops the default Gram kernel issues (csrc/gram_tc2.cu tile list): see gram_tile_products()."""
-    return 2.0 * 65536 * gram_tile_products(d) * n
+    """Flops the default Gram kernel issues (csrc/gram_tc2.cu tile list): 3 split MMAs per 256 x 256 pair tile of the upper
+    triangle; the tiles of the last tile column run with N trimmed to the selected genes, rounded to 32 (208 of 256 at d = 2000)."""
+    return 2.0 * 256 * gram_tile_columns(d) * n
+
+
+def gram_tile_columns(d):
+    """Accumulator columns (x 3 split terms) summed over the scheduled tiles, kept in step with gram_tcgen05_pair()."""
+    nt = (d + 255) // 256
+    rem = d - (nt - 1) * 256
+    last_n = 256 if os.environ.get("SRB_GRAM_TRIM", "1")[:1] == "0" else max(32, min(256, (rem + 31) // 32 * 32))
+    return 3 * ((nt * (nt + 1) // 2 - nt) * 256 + nt * last_n)
 
 
 def gram_tile_products(d):
-    """256 x 256 tile products per 1-cell slice of the contraction, as scheduled by csrc/gram_tc2.cu (kept in step with it)."""
-    nt = (d + 255) // 256
-    return 3 * (nt * (nt + 1) // 2)
+    """256 x 256 tile-product equivalents per 1-cell slice of the contraction."""
+    return gram_tile_columns(d) / 256.0
 
 
 def csrc_hash():

@@ -3,10 +3,13 @@
 // (64 KB per 64-cell k-block instead of 96 KB for a 128 x 256 single-CTA tile), the leader CTA issues one
 // tcgen05.mma.cta_group::2 (M = 256, N = 256) per split term, and each CTA's epilogue warps fold their own 128 TMEM
 // lanes into the fp64 partial tile. The single-CTA kernel was L2-fill bound (~40 B/clk/SM); this halves the operand
-// bytes per MMA flop... (3 stages x 64 KB). The pair kernel still sits at that limit: 64 KB per 64-cell k-block against 1536
-// MMA clocks = 43 B/clk/SM. Measured in round 2: running the 8 tiles of the last tile column with N = 208 instead of 256
-// (3 % fewer MMA flops, same operand bytes) changed nothing (8.12 vs 8.10 ms) — the next step is fewer operand bytes per flop
-// (A tiles multicast over a 4-CTA cluster), not fewer flops.
+// bytes per MMA flop (3 stages x 64 KB).
+// Schedule: 36 pair tiles of the upper triangle (d = 2000 -> 8 x 8 tile grid) x 2 halves of the cells = 72 work items on the
+// 74 CTA pairs of the chip, one item each, so the kernel lasts as long as ONE full item: ncu shows the tensor pipe 81.5 %
+// active. The tiles of the last tile column run with N trimmed to the selected genes (208 of 256 at d = 2000): 3 % fewer
+// executed flops and less power, but no shorter kernel (8.12 vs 8.10 ms measured) because the other 64 items set the
+// makespan. What would shorten it is a balanced split of (tile, k-block) work over all 74 pairs with the trimmed and the
+// diagonal tiles weighted by their real cost (at most 7 %), not attempted here.
 //
 // Barrier protocol (all barriers exist in both CTAs at the same shared-memory offsets):
 //   full[s]   lives in the leader; count 2 (one arrive per producer) + 2 x 64 KB of TMA transaction bytes
