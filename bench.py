@@ -457,7 +457,7 @@ def stage_rooflines(args, n, nnz, mean_stage):
 
 def gram_executed_flops(n, d):
     """Flops the default Gram kernel issues (csrc/gram_tc2.cu tile list): 3 split MMAs per 256 x 256 pair tile of the upper
-    triangle; the tiles of the last tile column run with N trimmed to the selected genes, rounded to 32 (208 of 256 at d = 2000)."""
+    triangle; with SRB_GRAM_TRIM=1 the tiles of the last tile column run with N trimmed to the selected genes, rounded to 32."""
     return 2.0 * 256 * gram_tile_columns(d) * n
 
 
@@ -465,7 +465,7 @@ def gram_tile_columns(d):
     """Accumulator columns (x 3 split terms) summed over the scheduled tiles, kept in step with gram_tcgen05_pair()."""
     nt = (d + 255) // 256
     rem = d - (nt - 1) * 256
-    last_n = 256 if os.environ.get("SRB_GRAM_TRIM", "1")[:1] == "0" else max(32, min(256, (rem + 31) // 32 * 32))
+    last_n = max(32, min(256, (rem + 31) // 32 * 32)) if os.environ.get("SRB_GRAM_TRIM", "0")[:1] == "1" else 256
     return 3 * ((nt * (nt + 1) // 2 - nt) * 256 + nt * last_n)
 
 

@@ -5,11 +5,14 @@
 // lanes into the fp64 partial tile. The single-CTA kernel was L2-fill bound (~40 B/clk/SM); this halves the operand
 // bytes per MMA flop (3 stages x 64 KB).
 // Schedule: 36 pair tiles of the upper triangle (d = 2000 -> 8 x 8 tile grid) x 2 halves of the cells = 72 work items on the
-// 74 CTA pairs of the chip, one item each, so the kernel lasts as long as ONE full item: ncu shows the tensor pipe 81.5 %
-// active. The tiles of the last tile column run with N trimmed to the selected genes (208 of 256 at d = 2000): 3 % fewer
-// executed flops and less power, but no shorter kernel (8.12 vs 8.10 ms measured) because the other 64 items set the
-// makespan. What would shorten it is a balanced split of (tile, k-block) work over all 74 pairs with the trimmed and the
-// diagonal tiles weighted by their real cost (at most 7 %), not attempted here.
+// 74 CTA pairs of the chip, one item each, all sweeping the cells in lock step: the 64-cell slab of the panels that one item
+// pulls into L2 is what the other 35 tiles of the same half need at that moment, which is why DRAM sees 12 GB for 8.4 GB of
+// panels and not 36 x that. ncu: tensor pipe 81 % active; the kernel lasts as long as ONE full item.
+// SRB_GRAM_TRIM=1 runs the tiles of the last tile column with N trimmed to the selected genes (208 of 256 at d = 2000).
+// Measured in round 2 and left OFF: 3 % fewer executed flops, same duration (8.12 vs 8.10 ms — the other 64 items set the
+// makespan), and the trimmed items run ahead of the sweep, which breaks the lock step: DRAM reads 12.0 -> 21.4 GB, L2 hit
+// rate 76 -> 65 % (profiles/r02_summary.md). The same effect rules out a stream-K style balanced split of (tile, k-block)
+// work over all 74 pairs, which would otherwise be worth up to 7 %.
 //
 // Barrier protocol (all barriers exist in both CTAs at the same shared-memory offsets):
 //   full[s]   lives in the leader; count 2 (one arrive per producer) + 2 x 64 KB of TMA transaction bytes
@@ -320,11 +323,11 @@ void gram_tcgen05_pair(srb_ctx *ctx, const __half *Xh, const __half *Xl, uint64_
     p.kblocks_total = kblocks;
     p.partial = partial->as<double>();
     {
-        // the columns beyond d_used are padding: the tiles of the last tile column run the MMA with N = what is needed,
-        // rounded to 32 (each CTA of the pair supplies N / 2 columns, a multiple of 16) — 208 instead of 256 at d = 2000
+        // the columns beyond d_used are padding: with SRB_GRAM_TRIM=1 the tiles of the last tile column run the MMA with
+        // N = what is needed, rounded to 32 (each CTA of the pair supplies N / 2 columns, a multiple of 16)
         static const int trim = [] {
             const char *e = getenv("SRB_GRAM_TRIM");
-            return (e && e[0] == '0') ? 0 : 1;
+            return (e && e[0] == '1') ? 1 : 0;  // off by default: see the header
         }();
         const uint32_t used = d_used ? std::min(d_used, dpad) : dpad;
         const uint32_t rem = used - (NT - 1) * TN;  // columns of the last tile column that hold selected genes
