@@ -479,7 +479,7 @@ def csrc_hash():
     h = hashlib.sha256()
     base = os.path.join(ROOT, "singlerust_b200", "csrc")
     for f in sorted(os.listdir(base)):
-        if f.endswith((".cu", ".cuh", ".cpp", ".h")):
+        if f.endswith((".cu", ".cuh")):  # device code only: host_pack.cpp cannot change a kernel's DRAM traffic
             with open(os.path.join(base, f), "rb") as fh:
                 h.update(fh.read())
     return h.hexdigest()

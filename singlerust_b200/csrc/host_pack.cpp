@@ -129,6 +129,18 @@ static HostPool &pool() {
     return *p;
 }
 
+// Parts per parallel region: 4 per thread (handed out dynamically by the pool), never smaller than `min_units`. With one
+// part per thread a region lasts as long as its slowest thread, and in the pipelined end-to-end step one of the cores is
+// shared with the host thread that drives the other batch's kernels: that thread's part took twice as long.
+static int region_parts(int nthreads, uint64_t n, int min_shift) {
+    static const int per_thread = [] {
+        const char *e = getenv("SRB_PACK_PARTS_PER_THREAD");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 16 ? v : 4;
+    }();
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads * (nthreads > 1 ? per_thread : 1), n >> min_shift));
+}
+
 // ---- the packing loops; cloned per ISA so the .so stays loadable on any x86-64 host -----------------------------
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
 #define SRB_ISA_CLONES __attribute__((target_clones("avx512f", "avx2", "default")))
@@ -168,7 +180,7 @@ bool host_pack_indices(const void *src, int src_width, uint64_t n, void *dst, in
     const uint64_t bm1 = bound - 1;
     if (nthreads <= 0) nthreads = host_pack_threads();
     // >= 64 K entries per part: below that the fork/join costs more than the copy
-    const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads, n >> 16));
+    const int parts = region_parts(nthreads, n, 16);
     if (parts == 1) return (pack_range(src, src_width, dst, dst_width, 0, n, bm1) >> 63) != 0;
     std::vector<uint64_t> acc((size_t)parts, 0);
     const uint64_t per = ((n + parts - 1) / parts + 63) & ~uint64_t(63);  // parts start on 64-entry boundaries
@@ -184,7 +196,7 @@ bool host_pack_indices(const void *src, int src_width, uint64_t n, void *dst, in
 void host_copy_parallel(const void *src, void *dst, uint64_t bytes, int nthreads) {
     if (bytes == 0) return;
     if (nthreads <= 0) nthreads = host_pack_threads();
-    const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads, bytes >> 19));
+    const int parts = region_parts(nthreads, bytes, 19);
     if (parts == 1) {
         memcpy(dst, src, bytes);
         return;
@@ -242,7 +254,7 @@ SRB_PACK_VALUES_LOOP(pack_f32_u16, uint16_t)
 bool host_pack_values_f32(const float *src, uint64_t n, void *dst, int dst_width, int nthreads) {
     if (n == 0) return true;
     if (nthreads <= 0) nthreads = host_pack_threads();
-    const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads, n >> 16));
+    const int parts = region_parts(nthreads, n, 16);
     auto one = [&](uint64_t a, uint64_t b) -> uint32_t {
         return dst_width == 1 ? pack_f32_u8(src + a, (uint8_t *)dst + a, b - a) : pack_f32_u16(src + a, (uint16_t *)dst + a, b - a);
     };
@@ -334,7 +346,7 @@ bool host_delta_encode(const void *cols, const void *offs, int width, uint64_t n
     if (bound > (1ull << 63)) bound = 1ull << 63;
     const uint64_t bm1 = bound - 1;
     if (nthreads <= 0) nthreads = host_pack_threads();
-    const int parts = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)nthreads, len >> 16));
+    const int parts = region_parts(nthreads, len, 16);
     std::vector<DeltaEscapes> pe((size_t)parts);
     std::vector<uint64_t> acc((size_t)parts, 0);
     const uint64_t per = ((len + parts - 1) / parts + 63) & ~uint64_t(63);
