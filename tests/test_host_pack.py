@@ -110,6 +110,48 @@ def test_delta_round_trip(dtype, chunk, threads):
     assert (codes == 255).sum() <= 300                                   # dense case: at most the line starts escape
 
 
+def delta_decode_fast(offsets, codes, esc_pos, esc_val):
+    """The same decoder, vectorised (segments restart at line starts and at escapes) for inputs of many parts."""
+    d = codes.astype(np.int64)
+    d[esc_pos.astype(np.int64)] = esc_val.astype(np.int64)
+    start = np.zeros(codes.shape[0], bool)
+    lens = np.diff(offsets.astype(np.int64))
+    start[offsets[:-1].astype(np.int64)[lens > 0]] = True
+    start[esc_pos.astype(np.int64)] = True
+    cs = np.cumsum(d)
+    first = np.nonzero(start)[0]
+    base = cs[first] - d[first]
+    return (cs - base[np.cumsum(start) - 1]).astype(np.uint64)
+
+
+@pytest.mark.parametrize("dtype", [np.uint64, np.uint32])
+@pytest.mark.parametrize("threads", [2, 3, 8])
+def test_delta_round_trip_many_parts(dtype, threads):
+    """Enough entries that one chunk is cut into several parts (>= 64 K entries each, up to 4 per thread): parts start in the
+    middle of a line, the escape lists of the parts are merged in entry order, empty lines sit on part boundaries."""
+    rng = np.random.default_rng(threads)
+    nrows, ncols = 1500, 30_000
+    lens = rng.poisson(450, nrows).clip(0, ncols)
+    lens[[0, 1, 700, 701, 702, nrows - 1]] = 0
+    lens[10] = 20_000                                                    # one line longer than a part
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    idx = np.concatenate([np.sort(rng.choice(ncols, L, replace=False)) for L in lens]).astype(np.uint64)
+    assert idx.shape[0] > 5 * 65536
+    small = delta_decode(off[:40], *(_ffi.host_delta_encode(off[:40].astype(dtype), idx[:int(off[39])].astype(dtype), ncols, 1 << 22, 1)[:3]))
+    np.testing.assert_array_equal(small, idx[:int(off[39])])             # the fast decoder's reference agrees with the slow one below
+    for chunk in (1 << 22, 200_000):
+        codes, pos, val, oob = _ffi.host_delta_encode(off.astype(dtype), idx.astype(dtype), ncols, chunk, threads)
+        assert not oob
+        assert np.all(np.diff(pos.astype(np.int64)) > 0)
+        assert np.array_equal(np.nonzero(codes == 255)[0], pos)
+        np.testing.assert_array_equal(delta_decode_fast(off, codes, pos, val), idx)
+    np.testing.assert_array_equal(delta_decode_fast(off[:40], *(_ffi.host_delta_encode(off[:40].astype(dtype), idx[:int(off[39])].astype(dtype), ncols, 1 << 22, 1)[:3])), small)
+    # an out-of-bounds index in the middle of a late part is reported
+    bad = idx.copy()
+    bad[-70_000] = ncols
+    assert _ffi.host_delta_encode(off.astype(dtype), bad.astype(dtype), ncols, 1 << 22, threads)[3] is True
+
+
 def test_delta_keeps_non_canonical_input_exact():
     """Duplicates (gap 0) and unsorted pairs (negative gap -> escape) must decode to exactly what the caller passed, so
     the device's canonical-form check still reports them."""
